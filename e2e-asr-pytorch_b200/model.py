@@ -1,0 +1,421 @@
+"""Plain-PyTorch acoustic model + RNNLM with the reference's module tree.
+
+These modules are NOT the accelerated path.  north_star keeps the VGG/BLSTM
+encoder, the location-aware attention decoder step and the RNNLM LSTM step as
+cuBLAS/cuDNN-backed PyTorch; they exist here so that
+
+* ``bench.py`` / ``smoke()`` can build the BASELINE configs on the GPU box,
+  where ``/root/reference`` is absent, with random-init weights, and
+* checkpoints of the reference load unchanged: parameter names and shapes
+  follow ``/root/reference/src/asr.py`` (ASR :13-52, Decoder :183-270,
+  Attention :273-364, Encoder :390-476), ``src/module.py`` (VGGExtractor
+  :659-716, RNNLayer :1003-1081, LocationAwareAttention :1135-1173,
+  ScaleDotAttention :1120-1132) and ``src/lm.py`` (RNNLM :5-38), so
+  ``ref_model.load_state_dict(our_model.state_dict())`` works both ways.
+
+The modules also expose the small stateful protocol the reference's
+``BeamDecoder`` drives (``decoder.init_state/get_state/set_state/get_query``,
+``attention.reset_mem/set_mem``, ``asr.set_state``): the CPU oracle
+(``oracle/beam_oracle.py``) uses it one hypothesis at a time, exactly like the
+reference.  The batched device beam search (``decode.py``/``stepper.py``) does
+not call these forward methods per hypothesis; it reads the weights and runs
+its own batched step.
+
+Supported subset (what the shipped configs under ``config/`` need for decode):
+encoder ``vgg`` 0/1 + (B)LSTM/GRU layers with drop/concat sub-sampling, optional
+LayerNorm and projection; attention ``loc`` or ``dot``; LSTM/GRU decoder; RNNLM
+LSTM/GRU with or without embedding tying.
+"""
+import math
+
+import numpy as np
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+FBANK_SIZE = 40   # src/option.py / module.py check_dim: fbank features come in blocks of 40
+
+
+def reference_init_(module):
+    """Weight init of ``src/util.py:60-83`` (Embedding ~ N(0,1); matrices and
+    conv kernels ~ N(0, 1/fan_in); biases zero), applied through
+    ``nn.Module.apply``."""
+    if isinstance(module, nn.Embedding):
+        module.weight.data.normal_(0, 1)
+        return
+    for p in module.parameters():
+        d = p.data
+        if d.dim() == 1:
+            d.zero_()
+        elif d.dim() == 2:
+            d.normal_(0, 1.0 / math.sqrt(d.size(1)))
+        elif d.dim() in (3, 4):
+            fan = d.size(1)
+            for k in d.size()[2:]:
+                fan *= k
+            d.normal_(0, 1.0 / math.sqrt(fan))
+        else:
+            raise NotImplementedError
+
+
+class VGGFrontEnd(nn.Module):
+    """2x(conv3x3,conv3x3,maxpool2) front end, 4x time reduction (module.py:659-716)."""
+
+    def __init__(self, input_dim):
+        super().__init__()
+        if input_dim % 13 == 0:
+            self.in_channel, self.freq_dim = input_dim // 13, 13
+        elif input_dim % FBANK_SIZE == 0:
+            self.in_channel, self.freq_dim = input_dim // FBANK_SIZE, FBANK_SIZE
+        else:
+            raise ValueError("VGG front end needs 13k (MFCC) or 40k (fbank) features, got %d" % input_dim)
+        c1, c2 = 128, 256
+        self.out_dim = (self.freq_dim // 4) * c2
+        self.extractor = nn.Sequential(
+            nn.Conv2d(self.in_channel, c1, 3, stride=1, padding=1), nn.ReLU(),
+            nn.Conv2d(c1, c1, 3, stride=1, padding=1), nn.ReLU(),
+            nn.MaxPool2d(2, stride=2, ceil_mode=True),
+            nn.Conv2d(c1, c2, 3, stride=1, padding=1), nn.ReLU(),
+            nn.Conv2d(c2, c2, 3, stride=1, padding=1), nn.ReLU(),
+            nn.MaxPool2d(2, stride=2, ceil_mode=True))
+
+    def _as_image(self, feat):
+        drop = feat.shape[1] % 4
+        if drop:
+            feat = feat[:, :-drop, :].contiguous()
+        n, t, _ = feat.shape
+        return feat.view(n, t, self.in_channel, self.freq_dim).transpose(1, 2)
+
+    def forward(self, feat, feat_len):
+        img = self.extractor(self._as_image(feat))              # [N, 256, T/4, F/4]
+        out = img.transpose(1, 2).contiguous()
+        return out.view(out.shape[0], out.shape[1], self.out_dim), feat_len // 4
+
+    def forward_masked(self, feat, feat_len):
+        """Batched variant for ragged utterances: activations beyond each
+        utterance's own length are zeroed after every convolution, so a padded
+        batch row sees the same zero padding a batch-1 call would."""
+        img = self._as_image(feat)
+        n, _, t, _ = img.shape
+        own = (feat_len // 4 * 4).to(img.device)          # a batch-1 call crops to a multiple of 4
+
+        def keep(a):
+            valid = own // (t // a.shape[2])
+            m = torch.arange(a.shape[2], device=a.device)[None, :] < valid[:, None]
+            return a * m[:, None, :, None].to(a.dtype)
+
+        img = keep(img)
+        for layer in self.extractor:
+            img = layer(img)
+            if isinstance(layer, nn.ReLU):
+                img = keep(img)
+        out = img.transpose(1, 2).contiguous()
+        return out.view(out.shape[0], out.shape[1], self.out_dim), feat_len // 4
+
+
+class RecurrentLayer(nn.Module):
+    """(B)LSTM/GRU + optional LayerNorm/dropout/sub-sampling/projection (module.py:1003-1081)."""
+
+    def __init__(self, input_dim, module, dim, bidirection, dropout, layer_norm, sample_rate, sample_style, proj):
+        super().__init__()
+        if sample_style not in ("drop", "concat"):
+            raise ValueError("Unsupported Sample Style: " + sample_style)
+        width = 2 * dim if bidirection else dim
+        self.out_dim = sample_rate * width if (sample_rate > 1 and sample_style == "concat") else width
+        self.sample_rate, self.sample_style = sample_rate, sample_style
+        self.dropout, self.layer_norm, self.proj = dropout, layer_norm, proj
+        self.layer = getattr(nn, module.upper())(input_dim, dim, bidirectional=bidirection, num_layers=1, batch_first=True)
+        if layer_norm:
+            self.ln = nn.LayerNorm(width)
+        if dropout > 0:
+            self.dp = nn.Dropout(p=dropout)
+        if proj:
+            self.pj = nn.Linear(width, width)
+
+    def _post(self, out, x_len):
+        if self.layer_norm:
+            out = self.ln(out)
+        if self.dropout > 0:
+            out = self.dp(out)
+        if self.sample_rate > 1:
+            n, t, d = out.shape
+            x_len = x_len // self.sample_rate
+            if self.sample_style == "drop":
+                out = out[:, ::self.sample_rate, :].contiguous()
+            else:
+                if t % self.sample_rate:
+                    out = out[:, :-(t % self.sample_rate), :]
+                out = out.contiguous().view(n, t // self.sample_rate, d * self.sample_rate)
+        if self.proj:
+            out = torch.tanh(self.pj(out))
+        return out, x_len
+
+    def forward(self, x, x_len):
+        out, _ = self.layer(x)                      # reference runs the padded batch unpacked
+        return self._post(out, x_len)
+
+    def forward_packed(self, x, x_len):
+        """Ragged batch: pack so that the backward direction of every utterance
+        starts at its own last frame (== what a batch-1 call computes)."""
+        t_max = x.shape[1]
+        packed = nn.utils.rnn.pack_padded_sequence(x, x_len.cpu().clamp(min=1), batch_first=True, enforce_sorted=False)
+        out, _ = self.layer(packed)
+        out, _ = nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=t_max)
+        return self._post(out, x_len)
+
+
+class Encoder(nn.Module):
+    """Listener (asr.py:390-476): optional VGG front end + recurrent stack."""
+
+    def __init__(self, input_size, batch_size, vgg, vgg_freq, vgg_low_filt, module, bidirection, dim, dropout,
+                 layer_norm, proj, sample_rate, sample_style):
+        super().__init__()
+        assert len(sample_rate) == len(dropout) == len(dim), "Number of layer mismatch"
+        self.vgg, self.vgg_freq, self.vgg_low_filt = vgg, vgg_freq, vgg_low_filt
+        self.sample_rate = 1
+        stack, width = [], input_size
+        if vgg == 1:
+            stack.append(VGGFrontEnd(input_size))
+            width = stack[-1].out_dim
+            self.sample_rate *= 4
+        elif vgg != 0:
+            raise NotImplementedError("vgg = {} front end is outside the decode hot path scope".format(vgg))
+        if module not in ("LSTM", "GRU"):
+            raise NotImplementedError("encoder module " + str(module))
+        for l in range(len(dim)):
+            stack.append(RecurrentLayer(width, module, dim[l], bidirection, dropout[l], layer_norm[l],
+                                        sample_rate[l], sample_style, proj[l]))
+            width = stack[-1].out_dim
+            self.sample_rate *= sample_rate[l]
+        self.in_dim, self.out_dim = input_size, width
+        self.layers = nn.ModuleList(stack)
+
+    def forward(self, x, x_len):
+        for layer in self.layers:
+            x, x_len = layer(x, x_len)
+        return x, x_len
+
+    def forward_ragged(self, x, x_len):
+        """Batched encode of zero-padded utterances of different lengths with
+        per-utterance results equal (up to library kernel selection) to
+        batch-1 calls: masked VGG + packed recurrent layers."""
+        for layer in self.layers:
+            if isinstance(layer, VGGFrontEnd):
+                x, x_len = layer.forward_masked(x, x_len)
+            else:
+                x, x_len = layer.forward_packed(x, x_len)
+        return x, x_len
+
+
+class _AttentionCore(nn.Module):
+    """Mask + temperature softmax + context (module.py:1084-1117)."""
+
+    def __init__(self, temperature, num_head):
+        super().__init__()
+        self.temperature, self.num_head = temperature, num_head
+        self.mask, self.k_len = None, None
+
+    def reset_mem(self):
+        self.mask, self.k_len = None, None
+
+    def set_mem(self, prev_att):
+        pass
+
+    def compute_mask(self, k, k_len):
+        self.k_len = k_len
+        n, t, _ = k.shape
+        pad = torch.arange(t, device=k_len.device)[None, :] >= k_len[:, None]
+        self.mask = pad[:, None, :].expand(n, self.num_head, t).reshape(-1, t)
+
+    def _attend(self, energy, value):
+        score = (energy / self.temperature).masked_fill(self.mask, -np.inf)
+        attn = torch.softmax(score, dim=-1)
+        return torch.bmm(attn.unsqueeze(1), value).squeeze(1), attn
+
+
+class ScaleDotAttention(_AttentionCore):
+    def forward(self, q, k, v):
+        energy = torch.bmm(q.unsqueeze(1), k.transpose(1, 2)).squeeze(1)
+        out, attn = self._attend(energy, v)
+        return out, attn.view(-1, self.num_head, k.shape[1])
+
+
+class LocationAwareAttention(_AttentionCore):
+    """energy = w^T tanh(key + query + U(F * prev_att))   (module.py:1135-1173)."""
+
+    def __init__(self, kernel_size, kernel_num, dim, num_head, temperature):
+        super().__init__(temperature, num_head)
+        self.prev_att = None
+        self.loc_conv = nn.Conv1d(num_head, kernel_num, kernel_size=2 * kernel_size + 1, padding=kernel_size, bias=False)
+        self.loc_proj = nn.Linear(kernel_num, dim, bias=False)
+        self.gen_energy = nn.Linear(dim, 1)
+        self.dim = dim
+
+    def reset_mem(self):
+        super().reset_mem()
+        self.prev_att = None
+
+    def set_mem(self, prev_att):
+        self.prev_att = prev_att
+
+    def forward(self, q, k, v):
+        nh, t, _ = k.shape
+        n = nh // self.num_head
+        if self.prev_att is None:                                   # uniform over the valid frames
+            self.prev_att = torch.zeros((n, self.num_head, t), device=k.device)
+            for i, sl in enumerate(self.k_len):
+                self.prev_att[i, :, :sl] = 1.0 / sl
+        loc = torch.tanh(self.loc_proj(self.loc_conv(self.prev_att).transpose(1, 2)))      # [n, t, dim]
+        loc = loc.unsqueeze(1).repeat(1, self.num_head, 1, 1).view(-1, t, self.dim)
+        energy = self.gen_energy(torch.tanh(k + q.unsqueeze(1) + loc)).squeeze(2)
+        out, attn = self._attend(energy, v)
+        attn = attn.view(n, self.num_head, t)
+        self.prev_att = attn
+        return out, attn
+
+
+class Attention(nn.Module):
+    """Query/key projections + attention core with cached keys (asr.py:273-364)."""
+
+    def __init__(self, v_dim, q_dim, mode, dim, num_head, temperature, v_proj, loc_kernel_size, loc_kernel_num):
+        super().__init__()
+        self.v_dim, self.dim, self.mode, self.num_head, self.v_proj = v_dim, dim, mode.lower(), num_head, v_proj
+        self.proj_q = nn.Linear(q_dim, dim * num_head)
+        self.proj_k = nn.Linear(v_dim, dim * num_head)
+        if v_proj:
+            self.proj_v = nn.Linear(v_dim, v_dim * num_head)
+        if self.mode == "dot":
+            self.att_layer = ScaleDotAttention(temperature, num_head)
+        elif self.mode == "loc":
+            self.att_layer = LocationAwareAttention(loc_kernel_size, loc_kernel_num, dim, num_head, temperature)
+        else:
+            raise NotImplementedError
+        if num_head > 1:
+            self.merge_head = nn.Linear(v_dim * num_head, v_dim)
+        self.key = self.value = self.mask = None
+
+    def reset_mem(self):
+        self.key = self.value = self.mask = None
+        self.att_layer.reset_mem()
+
+    def set_mem(self, prev_attn):
+        self.att_layer.set_mem(prev_attn)
+
+    def forward(self, dec_state, enc_feat, enc_len):
+        n, t, _ = enc_feat.shape
+        query = torch.tanh(self.proj_q(dec_state)).view(n * self.num_head, self.dim)
+        if self.key is None:
+            self.att_layer.compute_mask(enc_feat, enc_len.to(enc_feat.device))
+            self.key = torch.tanh(self.proj_k(enc_feat))
+            self.value = torch.tanh(self.proj_v(enc_feat)) if self.v_proj else enc_feat
+            if self.num_head > 1:
+                self.key = self.key.view(n, t, self.num_head, self.dim).permute(0, 2, 1, 3).contiguous().view(-1, t, self.dim)
+                if self.v_proj:
+                    self.value = self.value.view(n, t, self.num_head, self.v_dim).permute(0, 2, 1, 3).contiguous().view(-1, t, self.v_dim)
+                else:
+                    self.value = self.value.repeat(self.num_head, 1, 1)
+        context, attn = self.att_layer(query, self.key, self.value)
+        if self.num_head > 1:
+            context = self.merge_head(context.view(n, self.num_head * self.v_dim))
+        return attn, context
+
+
+class Decoder(nn.Module):
+    """Speller: RNN over [embedding ; context] + vocabulary projection (asr.py:183-270)."""
+
+    def __init__(self, batch_size, input_dim, vocab_size, module, dim, layer, dropout):
+        super().__init__()
+        if module not in ("LSTM", "GRU"):
+            raise NotImplementedError("decoder module " + str(module))
+        self.in_dim, self.layer, self.dim, self.dropout = input_dim, layer, dim, dropout
+        self.hidden_state = None
+        self.enable_cell = module == "LSTM"
+        self.layers = getattr(nn, module)(input_dim, dim, num_layers=layer, dropout=dropout, batch_first=True)
+        self.char_trans = nn.Linear(dim, vocab_size)
+        self.final_dropout = nn.Dropout(dropout)
+
+    def init_state(self, bs):
+        dev = next(self.parameters()).device
+        z = lambda: torch.zeros((self.layer, bs, self.dim), device=dev)
+        self.hidden_state = (z(), z()) if self.enable_cell else z()
+        return self.get_state()
+
+    def set_state(self, hidden_state):
+        dev = next(self.parameters()).device
+        if self.enable_cell:
+            self.hidden_state = (hidden_state[0].to(dev), hidden_state[1].to(dev))
+        else:
+            self.hidden_state = hidden_state.to(dev)
+
+    def get_state(self):
+        if self.enable_cell:
+            return (self.hidden_state[0].cpu(), self.hidden_state[1].cpu())
+        return self.hidden_state.cpu()
+
+    def get_query(self):
+        h = self.hidden_state[0] if self.enable_cell else self.hidden_state
+        return h.transpose(0, 1).reshape(-1, self.dim * self.layer)
+
+    def forward(self, x):
+        x, self.hidden_state = self.layers(x.unsqueeze(1), self.hidden_state)
+        x = x.squeeze(1)
+        return self.char_trans(self.final_dropout(x)), x
+
+
+class ASR(nn.Module):
+    """Joint CTC/attention model container (asr.py:13-64).  Only what decoding
+    needs: the training ``forward`` of the reference is out of scope."""
+
+    def __init__(self, input_size, vocab_size, batch_size, ctc_weight, encoder, attention, decoder,
+                 emb_drop=0.0, init_adadelta=True):
+        super().__init__()
+        assert 0 <= ctc_weight <= 1
+        self.vocab_size, self.ctc_weight = vocab_size, ctc_weight
+        self.enable_ctc, self.enable_att = ctc_weight > 0, ctc_weight != 1
+        self.lm = None
+        self.encoder = Encoder(input_size, batch_size, **encoder)
+        if self.enable_ctc:
+            self.ctc_layer = nn.Sequential(nn.Linear(self.encoder.out_dim, vocab_size), nn.ReLU())   # asr.py:29-32
+        if self.enable_att:
+            self.dec_dim = decoder["dim"]
+            self.pre_embed = nn.Embedding(vocab_size, self.dec_dim)
+            self.embed_drop = nn.Dropout(emb_drop)
+            self.decoder = Decoder(batch_size, self.encoder.out_dim + self.dec_dim, vocab_size, **decoder)
+            self.attention = Attention(self.encoder.out_dim, self.dec_dim * self.decoder.layer, **attention)
+        # asr.py:44-50: the reference always applies its own init + forget-gate bias 1
+        self.apply(reference_init_)
+        if self.enable_att and self.decoder.enable_cell:
+            for l in range(self.decoder.layer):
+                b = getattr(self.decoder.layers, "bias_ih_l{}".format(l))
+                n = b.size(0)
+                b.data[n // 4:n // 2].fill_(1.0)
+
+    def set_state(self, prev_state, prev_attn):
+        self.decoder.set_state(prev_state)
+        self.attention.set_mem(prev_attn)
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("training forward (asr.py:89-177) is outside the decode hot-path scope")
+
+
+class RNNLM(nn.Module):
+    """Embedding -> n-layer LSTM/GRU -> tied or separate output layer (lm.py:5-38)."""
+
+    def __init__(self, vocab_size, emb_tying, emb_dim, module, dim, n_layers, dropout):
+        super().__init__()
+        self.dim, self.n_layers, self.emb_tying, self.vocab_size = dim, n_layers, emb_tying, vocab_size
+        if emb_tying:
+            assert emb_dim == dim, "Output dim of RNN should be identical to embedding if using weight tying."
+        self.emb = nn.Embedding(vocab_size, emb_dim)
+        self.dp1, self.dp2 = nn.Dropout(dropout), nn.Dropout(dropout)
+        self.rnn = getattr(nn, module.upper())(emb_dim, dim, num_layers=n_layers, dropout=dropout, batch_first=True)
+        if not emb_tying:
+            self.trans = nn.Linear(emb_dim, vocab_size)
+
+    def forward(self, x, lens, hidden=None):
+        emb = self.dp1(self.emb(x))
+        packed = nn.utils.rnn.pack_padded_sequence(emb, lens, batch_first=True, enforce_sorted=False)
+        out, hidden = self.rnn(packed, hidden)
+        out, _ = nn.utils.rnn.pad_packed_sequence(out, batch_first=True)
+        out = F.linear(self.dp2(out), self.emb.weight) if self.emb_tying else self.trans(self.dp2(out))
+        return out, hidden
