@@ -1,0 +1,266 @@
+// Kernel (2): batched CTC prefix-score recursion.
+// Replaces CTCPrefixScore.cheap_compute / full_compute (src/ctc.py:29-108) for every live
+// (utterance, beam slot, candidate) in one launch.
+//
+// Mapping.  One thread owns one prefix-state lane l = slot*C + j of one utterance and walks the
+// encoder frames t = start..T-1 sequentially in fp32 (the reference's order), carrying
+// (r_nonblank, r_blank, psi) in registers.  A CTA covers `blockDim.x` consecutive lanes of ONE
+// utterance, so all of its threads share the utterance's posterior rows x[t][u][:] and the few
+// parent states r_prev[t][parent].  Frames are processed in tiles of kTile:
+//   * "rows" variant (Vp <= kMaxRowFloats): the tile's posterior rows are brought into shared
+//     memory by the TMA engine (cp.async.bulk, one 16B-aligned row per copy, completion on an
+//     mbarrier), double buffered, so the gather x[t][cand] becomes a conflict-free LDS;
+//   * "gather" variant (large vocabularies): each lane fetches its own column x[t][u][cand]
+//     for the whole tile with independent loads and parks them in shared memory.
+//   Per tile the CTA first turns the parents' states into phi tiles in shared memory
+//     phi[h][t] = ( logaddexp(r_prev[t][0], r_prev[t][1]),  r_prev[t][1] )
+//   (once per hypothesis instead of once per candidate), then every lane runs
+//     r0' = logaddexp(r0, phi) + x_c ; r1' = logaddexp(r1, r0) + x_blank ; psi = logaddexp(psi, phi + x_c)
+//   and streams (r0', r1') out as one coalesced float2 per lane per frame.
+#include "common.cuh"
+
+namespace e2e {
+
+constexpr int kTile = 32;            // frames per shared-memory tile
+constexpr int kMaxRowFloats = 256;   // rows variant up to 1 KB per posterior row
+constexpr int kMaxThreads = 256;
+
+struct PrefixParams {
+    const float *x; int Tmax, U, Vp, V;
+    const int *enc_len;
+    const float2 *r_prev; int lanes_prev;
+    const int *prev_lane, *last_tok, *prefix_len, *n_live, *cand;
+    int B, C, flags;
+    float *psi; float2 *r_out; int *status;
+    int chunks_per_utt;   // CTAs per utterance
+    int hyps_per_cta;     // rows of the phi tile
+};
+
+template <bool kGather, bool kFast>
+__global__ void __launch_bounds__(kMaxThreads)
+prefix_score_kernel(const PrefixParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int u = blockIdx.x / p.chunks_per_utt;
+    const int chunk = blockIdx.x % p.chunks_per_utt;
+    const int T = p.enc_len ? p.enc_len[u] : p.Tmax;
+    const int live = p.n_live ? p.n_live[u] : p.B;
+    const int C = p.C, LU = p.B * p.C;
+    const int lane0 = chunk * nt;                 // first lane (within the utterance) of this CTA
+    if (T <= 0 || lane0 >= live * C) return;      // nothing to do for this CTA (uniform exit)
+    const bool full = (p.flags & E2E_PREFIX_FULL) != 0;
+    const bool fill_dead = (p.flags & E2E_PREFIX_SKIP_DEAD_ROWS) == 0;
+
+    // ---- shared memory carve-up -------------------------------------------------------------
+    // rows:   xs[2][kTile][Vp] | phis[H][kTile] float2 | s_plane[H] | s_red[2] | bars[2]
+    // gather: xs[kTile][nt]    | xb[kTile] | phis | s_plane | s_red
+    const int H = p.hyps_per_cta;
+    float *xs = reinterpret_cast<float *>(smem_raw);
+    const size_t xs_floats = kGather ? (size_t)kTile * nt + kTile : (size_t)2 * kTile * p.Vp;
+    float2 *phis = reinterpret_cast<float2 *>(xs + ((xs_floats + 3) & ~(size_t)3));
+    int *s_plane = reinterpret_cast<int *>(phis + (size_t)H * kTile);
+    int *s_red = s_plane + H;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_red + 2 + ((H & 1) ? 1 : 0));   // 8-byte aligned
+    float *xb_g = xs + (size_t)kTile * nt;       // gather variant only
+
+    // ---- per-lane setup ---------------------------------------------------------------------
+    const int lane_u = lane0 + tid;               // lane within the utterance
+    const bool active = lane_u < live * C;
+    const int h = active ? lane_u / C : 0;        // beam slot
+    const int j = active ? lane_u - h * C : 0;    // candidate index
+    const int h_lo = lane0 / C;
+    const int n = u * p.B + h;                    // hypothesis index
+    int tok = 0, plen = 0, ltok = 0;
+    if (active) {
+        tok = full ? j : p.cand[(long long)n * C + j];
+        plen = p.prefix_len[n];
+        ltok = p.last_tok[n];
+    }
+    const int start = plen > 1 ? plen : 1;
+    bool too_long = active && (start - 1 >= T);
+    if (too_long && p.status) atomicOr(p.status + u, E2E_STATUS_PREFIX_TOO_LONG);
+    const bool run = active && !too_long;
+    const bool special = full ? (tok == (plen > 0 ? ltok : 0)) : (plen > 0 && tok == ltok);
+
+    if (tid == 0) { s_red[0] = 0x7fffffff; }
+    for (int i = tid; i < H; i += nt) {
+        const int hh = h_lo + i;
+        s_plane[i] = (hh < live) ? p.prev_lane[u * p.B + hh] : -1;
+    }
+    if (!kGather && tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (run) atomicMin(&s_red[0], start);
+    __syncthreads();
+    const int cta_start = s_red[0];               // 0x7fffffff if no lane runs
+    const long long xrow0 = (long long)u * p.Vp;  // x[t][u][:] = x + t*U*Vp + xrow0
+    const long long xstride = (long long)p.U * p.Vp;
+    float2 *__restrict__ rout = p.r_out + ((long long)u * p.Tmax) * LU + lane_u;
+    const float2 *__restrict__ rprev_u = p.r_prev + ((long long)u * p.Tmax) * p.lanes_prev;
+    const float2 dead = make_float2(E2E_CTC_LOGZERO, E2E_CTC_LOGZERO);
+
+    float nb = E2E_CTC_LOGZERO, bl = E2E_CTC_LOGZERO, psi = E2E_CTC_LOGZERO;
+    if (run && plen == 0) nb = __ldg(p.x + xrow0 + tok);     // r[0,0,:] = x[0, c]  (src/ctc.py:82-83)
+    psi = nb;                                                  // psi = r[start-1, 0, :] (src/ctc.py:85)
+
+    if (cta_start != 0x7fffffff) {
+        const int first_tile = cta_start / kTile;
+        const int n_tiles = (T + kTile - 1) / kTile;
+        // rows below the first computed tile are log-zero by construction
+        if (run && fill_dead)
+            for (int t = 0; t < first_tile * kTile && t < T; ++t) rout[(long long)t * LU] = dead;
+
+        auto issue_rows = [&](int k) {   // warp 0: one bulk copy per posterior row of tile k
+            const int t0 = k * kTile;
+            const int rows = min(kTile, T - t0);
+            uint64_t *bar = &bars[k & 1];
+            float *dst = xs + (size_t)(k & 1) * kTile * p.Vp;
+            if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)rows * p.Vp * 4u);
+            __syncwarp();
+            if (tid < rows)
+                bulk_g2s(dst + (size_t)tid * p.Vp, p.x + (long long)(t0 + tid) * xstride + xrow0, (uint32_t)p.Vp * 4u, bar);
+        };
+        if (!kGather && tid < 32 && first_tile < n_tiles) {
+            issue_rows(first_tile);
+            if (first_tile + 1 < n_tiles) issue_rows(first_tile + 1);
+        }
+
+        uint32_t parity[2] = {0u, 0u};
+        for (int k = first_tile; k < n_tiles; ++k) {
+            const int t0 = k * kTile;
+            const int rows = min(kTile, T - t0);
+            // -- phi tile: entry (hl, tt) describes r_prev at frame t0+tt-1 -----------------------
+            for (int i = tid; i < H * kTile; i += nt) {
+                const int hl = i / kTile, tt = i - hl * kTile;
+                const int ts = t0 + tt - 1;
+                const int pl = s_plane[hl];
+                if (pl >= 0 && ts >= 0 && ts < T && tt < rows) {
+                    const float2 a = __ldg(rprev_u + (long long)ts * p.lanes_prev + pl);
+                    float2 ph;
+                    ph.x = logaddexp<kFast>(a.x, a.y);
+                    ph.y = full ? logaddexp<kFast>(E2E_CTC_LOGZERO, a.y) : a.y;
+                    phis[i] = ph;
+                }
+            }
+            const float *xt;   // tile base: xt[tt*pitch + col]
+            int pitch, col;
+            if (kGather) {
+                if (active) {
+#pragma unroll 8
+                    for (int tt = 0; tt < rows; ++tt)
+                        xs[tt * nt + tid] = __ldg(p.x + (long long)(t0 + tt) * xstride + xrow0 + tok);
+                }
+                if (tid < rows) xb_g[tid] = __ldg(p.x + (long long)(t0 + tid) * xstride + xrow0 + E2E_CTC_BLANK);
+                xt = xs; pitch = nt; col = tid;
+            } else {
+                mbar_wait(&bars[k & 1], parity[k & 1]);
+                parity[k & 1] ^= 1u;
+                xt = xs + (size_t)(k & 1) * kTile * p.Vp; pitch = p.Vp; col = tok;
+            }
+            __syncthreads();
+            if (run) {
+                const float2 *ph_row = phis + (size_t)(h - h_lo) * kTile;
+                int tt = 0;
+                const int tt_first = start - t0;              // first frame of this tile that is computed
+                if (tt_first > 0) {
+                    const int stop = min(tt_first, rows);
+                    if (fill_dead)
+                        for (; tt < stop; ++tt)
+                            rout[(long long)(t0 + tt) * LU] = (t0 + tt == 0 && plen == 0) ? make_float2(nb, E2E_CTC_LOGZERO) : dead;
+                    tt = stop;
+                }
+#pragma unroll 4
+                for (; tt < rows; ++tt) {
+                    const float2 ph = ph_row[tt];
+                    const float phi = special ? ph.y : ph.x;
+                    const float xc = xt[tt * pitch + col];
+                    const float xb = kGather ? xb_g[tt] : xt[tt * pitch + E2E_CTC_BLANK];
+                    const float nnb = __fadd_rn(logaddexp<kFast>(nb, phi), xc);
+                    const float nbl = __fadd_rn(logaddexp<kFast>(bl, nb), xb);
+                    psi = logaddexp<kFast>(psi, __fadd_rn(phi, xc));
+                    nb = nnb; bl = nbl;
+                    rout[(long long)(t0 + tt) * LU] = make_float2(nnb, nbl);
+                }
+            }
+            __syncthreads();
+            if (!kGather && tid < 32 && k + 2 < n_tiles) issue_rows(k + 2);
+        }
+    }
+
+    if (run) {
+        if (!full && tok == E2E_CTC_EOS) {       // P(<eos> | g) = P(g)   (src/ctc.py:106-107)
+            const float2 a = __ldg(rprev_u + (long long)(T - 1) * p.lanes_prev + s_plane[h - h_lo]);
+            psi = logaddexp<kFast>(a.x, a.y);
+            // psi aliases r[start-1,0,:] in the reference when the time loop never runs (src/ctc.py:85)
+            if (start >= T && fill_dead) rout[(long long)(start - 1) * LU] = make_float2(psi, E2E_CTC_LOGZERO);
+        }
+        p.psi[(long long)n * C + j] = psi;
+    } else if (active) {
+        p.psi[(long long)n * C + j] = E2E_CTC_LOGZERO;
+    }
+}
+
+static size_t prefix_smem_bytes(bool gather, int nt, int Vp, int H)
+{
+    size_t xs_floats = gather ? (size_t)kTile * nt + kTile : (size_t)2 * kTile * Vp;
+    xs_floats = (xs_floats + 3) & ~(size_t)3;
+    size_t b = xs_floats * 4 + (size_t)H * kTile * 8 + (size_t)H * 4 + 8 + ((H & 1) ? 4 : 0) + 16;
+    return (b + 15) & ~(size_t)15;
+}
+
+}  // namespace e2e
+
+extern "C" int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int V, const int *enc_len,
+                                    const float *r_prev, int lanes_prev,
+                                    const int *prev_lane, const int *last_tok, const int *prefix_len,
+                                    const int *n_live, const int *cand, int B, int C, int flags,
+                                    float *psi, float *r_out, int *status, void *stream)
+{
+    using namespace e2e;
+    const bool full = (flags & E2E_PREFIX_FULL) != 0;
+    if (!x || !r_prev || !prev_lane || !last_tok || !prefix_len || !psi || !r_out || (!full && !cand))
+        return set_error(E2E_ERR_ARG, "e2e_ctc_prefix_score: null pointer");
+    if (Tmax <= 0 || U <= 0 || V <= 0 || B <= 0 || C <= 0 || lanes_prev <= 0)
+        return set_error(E2E_ERR_ARG, "e2e_ctc_prefix_score: non-positive size");
+    if (Vp != e2e_padded_vocab(V)) return set_error(E2E_ERR_ARG, "e2e_ctc_prefix_score: Vp=%d, expected %d", Vp, e2e_padded_vocab(V));
+    if (full && C != V) return set_error(E2E_ERR_ARG, "e2e_ctc_prefix_score: E2E_PREFIX_FULL needs C == V");
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(r_out) & 7) || (reinterpret_cast<uintptr_t>(r_prev) & 7))
+        return set_error(E2E_ERR_ARG, "e2e_ctc_prefix_score: misaligned buffer");
+
+    const long long LU = (long long)B * C;
+    int nt = (int)((LU + 31) / 32 * 32);
+    if (nt > kMaxThreads) {
+        // split the utterance's lanes over several CTAs of equal, warp-multiple size
+        const int chunks = (int)((LU + kMaxThreads - 1) / kMaxThreads);
+        nt = (int)(((LU + chunks - 1) / chunks + 31) / 32 * 32);
+    }
+    PrefixParams p;
+    p.x = x; p.Tmax = Tmax; p.U = U; p.Vp = Vp; p.V = V; p.enc_len = enc_len;
+    p.r_prev = reinterpret_cast<const float2 *>(r_prev); p.lanes_prev = lanes_prev;
+    p.prev_lane = prev_lane; p.last_tok = last_tok; p.prefix_len = prefix_len; p.n_live = n_live; p.cand = cand;
+    p.B = B; p.C = C; p.flags = flags;
+    p.psi = psi; p.r_out = reinterpret_cast<float2 *>(r_out); p.status = status;
+    p.chunks_per_utt = (int)((LU + nt - 1) / nt);
+    p.hyps_per_cta = (nt + C - 1) / C + 1;
+    if (p.hyps_per_cta > B) p.hyps_per_cta = B;
+    const long long grid = (long long)U * p.chunks_per_utt;
+    if (grid > 0x7fffffffLL) return set_error(E2E_ERR_UNSUPPORTED, "e2e_ctc_prefix_score: grid too large");
+
+    const bool gather = Vp > kMaxRowFloats;
+    const bool fast = (flags & E2E_PREFIX_FAST_MATH) != 0;
+    const size_t smem = prefix_smem_bytes(gather, nt, Vp, p.hyps_per_cta);
+    void (*kern)(PrefixParams) = gather ? (fast ? prefix_score_kernel<true, true> : prefix_score_kernel<true, false>)
+                                        : (fast ? prefix_score_kernel<false, true> : prefix_score_kernel<false, false>);
+    if (smem > 48 * 1024) {
+        if (smem > 200 * 1024) return set_error(E2E_ERR_UNSUPPORTED, "e2e_ctc_prefix_score: %zu bytes of shared memory needed", smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(E2E_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    kern<<<(unsigned)grid, nt, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    count_launch();
+    return check_launch("e2e_ctc_prefix_score");
+}

@@ -1,0 +1,223 @@
+"""Drop-in ``BeamDecoder`` / ``Hypothesis`` running the joint CTC/attention(+RNNLM)
+beam search batched over utterances on one B200.
+
+Mirrors the interface of ``/root/reference/src/decode.py``:
+
+* ``BeamDecoder(asr, emb_decoder, beam_size, min_len_ratio, max_len_ratio,
+  lm_path='', lm_config='', lm_weight=0.0, ctc_weight=0.0)``      (decode.py:17-48)
+* ``.forward(audio_feature[1,L,D], feature_len[1]) -> list[Hypothesis]`` best first
+  (decode.py:65-183), ``.create_msg()`` (decode.py:50-63) and the public attributes
+  ``beam_size, min_len_ratio, max_len_ratio, asr, apply_ctc, ctc_w, ctc_beam_size,
+  apply_lm, lm_w, lm_path, lm, apply_emb``
+* ``Hypothesis.outIndex`` / ``.avgScore()`` / ``.output_seq`` / ``.output_scores``
+  (decode.py:186-217,279-281)
+
+so ``bin/test_asr.py:80-82,159-173`` can use it unchanged.  In addition
+``decode_batch(features[U,Lmax,D], lengths[U])`` decodes many utterances at once —
+the reference fans single utterances out to joblib processes
+(``bin/test_asr.py:138-139``); here they share every kernel launch.
+
+Per decode step the device runs: the batched PyTorch model step (``stepper.py``),
+then (3a) ``e2e_beam_candidates``, (2) ``e2e_ctc_prefix_score``, (3b)
+``e2e_beam_combine_prune``; the posteriors come from (1) ``e2e_ctc_log_softmax``
+once per batch.  Nothing is copied to the host until the final N-best.
+There is no CPU fallback: inputs must live on a CUDA device.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+import yaml
+from torch import nn
+
+from . import _lib as L
+from . import ops
+from .model import RNNLM
+from .stepper import BatchedStepper
+
+CTC_BEAM_RATIO = 1.5      # decode.py:10
+LOG_ZERO = -10000000.0    # decode.py:11
+EOS_THRESHOLD = 1.5       # decode.py:220
+
+
+class Hypothesis:
+    """Result record with the reference's read interface (decode.py:186-217,279-281)."""
+
+    def __init__(self, tokens, scores, avg):
+        self._tokens = np.asarray(tokens, dtype=np.int64)
+        self._scores = np.asarray(scores, dtype=np.float32)
+        self._avg = np.float32(avg)
+
+    @property
+    def outIndex(self):
+        return [int(t) for t in self._tokens]
+
+    @property
+    def output_seq(self):
+        return [torch.tensor(int(t)) for t in self._tokens]
+
+    @property
+    def output_scores(self):
+        return [torch.tensor(float(s), dtype=torch.float32) for s in self._scores]
+
+    def avgScore(self):
+        assert len(self._scores) != 0
+        return torch.tensor(float(self._avg), dtype=torch.float32)
+
+    def __repr__(self):
+        return "Hypothesis(len=%d, avg=%.6f)" % (len(self._tokens), float(self._avg))
+
+
+class _Fp32Math:
+    """The reference computes in fp32 on the CPU; keep cuBLAS/cuDNN out of TF32."""
+
+    def __enter__(self):
+        self.prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = self.prev
+
+
+class BeamDecoder(nn.Module):
+    ''' Beam decoder for ASR (batched, device resident) '''
+
+    def __init__(self, asr, emb_decoder, beam_size, min_len_ratio, max_len_ratio,
+                 lm_path='', lm_config='', lm_weight=0.0, ctc_weight=0.0):
+        super().__init__()
+        self.beam_size = beam_size
+        self.min_len_ratio = min_len_ratio
+        self.max_len_ratio = max_len_ratio
+        self.asr = asr
+        assert self.asr.enable_att                                     # decode.py:27
+        if not 1 <= beam_size <= 32:
+            raise ValueError("beam_size must be in 1..32 (one warp per hypothesis, <=32 warps per CTA)")
+
+        self.apply_ctc = ctc_weight > 0
+        if self.apply_ctc:
+            assert self.asr.ctc_weight > 0, 'ASR was not trained with CTC decoder'   # decode.py:32
+            self.ctc_w = ctc_weight
+            self.ctc_beam_size = int(CTC_BEAM_RATIO * self.beam_size)
+
+        self.apply_lm = lm_weight > 0
+        if self.apply_lm:
+            self.lm_w = lm_weight
+            self.lm_path = lm_path
+            cfg = yaml.load(open(lm_config, 'r'), Loader=yaml.FullLoader)
+            self.lm = RNNLM(self.asr.vocab_size, **cfg['model'])
+            self.lm.load_state_dict(torch.load(self.lm_path, map_location='cpu')['model'])
+            self.lm.eval()
+
+        self.apply_emb = emb_decoder is not None
+        if self.apply_emb:
+            raise NotImplementedError("embedding-fusion decoding (src/plugin.py) is outside the decode hot-path scope")
+
+        # knobs of the device path (not part of the reference interface)
+        self.fast_math = False          # MUFU log-add-exp in the prefix-score kernel
+        self.skip_dead_rows = True      # do not write state rows t < len(prefix) nobody reads back
+        self.last_stats = {}
+
+    def create_msg(self):
+        msg = ['Decode spec| Beam size = {}\t| Min/Max len ratio = {}/{}'.format(
+            self.beam_size, self.min_len_ratio, self.max_len_ratio)]
+        if self.apply_ctc:
+            msg.append('           |Joint CTC decoding enabled \t| weight = {:.2f}\t'.format(self.ctc_w))
+        if self.apply_lm:
+            msg.append('           |Joint LM decoding enabled \t| weight = {:.2f}\t| src = {}'.format(self.lm_w, self.lm_path))
+        return msg
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, audio_feature, feature_len):
+        assert audio_feature.shape[0] == 1, "Batchsize == 1 is required for beam search"   # decode.py:67
+        return self.decode_batch(audio_feature, feature_len)[0]
+
+    @torch.no_grad()
+    def decode_batch(self, audio_feature, feature_len, return_arrays=False):
+        """audio_feature [U,Lmax,D] (zero padded), feature_len [U] -> list (per utterance) of
+        N-best ``Hypothesis`` lists, best first.  ``return_arrays=True`` returns the raw
+        (tokens, scores, lens, avg, n) CPU tensors instead (used by the sharded driver)."""
+        if not audio_feature.is_cuda:
+            raise L.E2EError("BeamDecoder has no CPU path: move the features and the decoder to a CUDA device")
+        dev = audio_feature.device
+        n_utts = audio_feature.shape[0]
+        beam = self.beam_size
+        vocab = self.asr.vocab_size
+        n_cand = self.ctc_beam_size if self.apply_ctc else 0
+        ctc_w = self.ctc_w if self.apply_ctc else 0.0
+        lm_w = self.lm_w if self.apply_lm else 0.0
+        lens_cpu = feature_len.detach().cpu().long()
+        # decode.py:74-78: output length limits come from the INPUT length
+        max_len = torch.tensor([int(np.ceil(int(l) * self.max_len_ratio)) for l in lens_cpu], dtype=torch.int32)
+        min_len = torch.tensor([int(np.ceil(int(l) * self.min_len_ratio)) for l in lens_cpu], dtype=torch.int32)
+        n_steps = int(max_len.max()) if n_utts else 0
+
+        with _Fp32Math():
+            stepper = BatchedStepper(self.asr, self.lm if self.apply_lm else None)
+            enc, enc_len = stepper.encode(audio_feature, feature_len.to(dev))
+            enc_len32 = enc_len.to(torch.int32).contiguous()
+            stepper.start(enc, enc_len, beam)
+            t_max = enc.shape[1]
+            buf = ops.BeamBuffers(n_utts, beam, n_cand, n_steps, min_len, max_len, dev)
+            r_prev = r_a = r_b = x = None
+            if self.apply_ctc:
+                lin = self.asr.ctc_layer[0]
+                logits = F.linear(enc, lin.weight, lin.bias).contiguous()          # cuBLAS; ReLU + log-softmax fused in (1)
+                x = ops.ctc_log_softmax(logits, enc_len32, apply_relu=True)        # decode.py:94-95
+                r_prev = ops.ctc_init_state(x, enc_len32)                          # decode.py:97
+                r_a = torch.empty((n_utts, t_max, beam * n_cand, 2), dtype=torch.float32, device=dev)
+                r_b = torch.empty_like(r_a)
+            pflags = (L.PREFIX_FAST_MATH if self.fast_math else 0) | (L.PREFIX_SKIP_DEAD_ROWS if self.skip_dead_rows else 0)
+
+            for step in range(n_steps):                                            # decode.py:104
+                att_logits, lm_logits = stepper.step(buf.last_tok.view(-1).long())
+                ops.beam_candidates(att_logits, n_utts, beam, vocab, n_cand, buf.n_active, buf.att_stats, buf.cand)
+                if self.apply_ctc:
+                    r_cur = r_a if (step % 2 == 0) else r_b
+                    ops.ctc_prefix_score(x, vocab, enc_len32, r_prev, buf.prev_lane.view(-1), buf.last_tok.view(-1),
+                                         buf.prefix_len.view(-1), buf.n_active, buf.cand, beam, n_cand, pflags,
+                                         psi=buf.psi, r_out=r_cur, status=buf.status)
+                    r_prev = r_cur
+                ops.beam_combine_prune(buf, att_logits, lm_logits, vocab, step, ctc_w, lm_w, EOS_THRESHOLD)
+                stepper.reorder(buf.parent_slot)
+
+            tok, sc, ln, avg, n = ops.beam_finalize(buf)
+            status = buf.status.cpu()
+            tok, sc, ln, avg, n = tok.cpu(), sc.cpu(), ln.cpu(), avg.cpu(), n.cpu()
+
+        self._raise_like_reference(status, n, max_len)
+        enc_len_cpu = enc_len.cpu()
+        self.last_stats = {
+            "utterances": n_utts, "steps": n_steps, "enc_frames": [int(t) for t in enc_len_cpu],
+            # unit count of SURVEY.md §8d: sum_s H_s * C * T per utterance
+            "cand_frames": int(sum((1 + (int(s) - 1) * beam) * n_cand * int(t)
+                                   for s, t in zip(max_len, enc_len_cpu) if int(s) > 0)) if self.apply_ctc else 0,
+        }
+        if return_arrays:
+            return tok, sc, ln, avg, n
+        return nbest_from_arrays(tok, sc, ln, avg, n)
+
+    @staticmethod
+    def _raise_like_reference(status, n_out, max_len):
+        bad = status.nonzero().reshape(-1).tolist()
+        for u in bad:
+            s = int(status[u])
+            if s & L.STATUS_PREFIX_TOO_LONG:
+                raise IndexError("utterance %d: hypothesis longer than the encoder output "
+                                 "(src/ctc.py:85; needs ceil(L*max_len_ratio) <= T_enc)" % u)
+            if s & L.STATUS_TOKEN_NOT_CAND:
+                raise ValueError("utterance %d: beam winner is not in the CTC candidate list "
+                                 "(src/decode.py:252: x is not in list)" % u)
+            if s & L.STATUS_FINISHED_OVERFLOW:
+                raise L.E2EError("utterance %d: finished-hypothesis buffer overflow" % u)
+
+
+def nbest_from_arrays(tok, sc, ln, avg, n):
+    out = []
+    tok, sc, ln, avg, n = (a.numpy() for a in (tok, sc, ln, avg, n))
+    for u in range(tok.shape[0]):
+        hyps = []
+        for k in range(int(n[u])):
+            m = int(ln[u, k])
+            hyps.append(Hypothesis(tok[u, k, :m], sc[u, k, :m], avg[u, k]))
+        out.append(hyps)
+    return out

@@ -1,0 +1,164 @@
+"""Typed torch-tensor wrappers over the C ABI (include/e2e_asr_b200.h).
+
+PyTorch is only the plumbing here: it owns the device buffers and the stream;
+every function below validates its tensors and enqueues ONE hand-written kernel
+through ctypes.  Nothing in this module computes on the CPU.
+"""
+import torch
+
+from . import _lib as L
+
+I32, F32 = torch.int32, torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype, name, numel=None):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise L.E2EError("%s must be a CUDA tensor (no CPU path)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    if numel is not None and t.numel() < numel:
+        raise ValueError("%s has %d elements, needs %d" % (name, t.numel(), numel))
+
+
+def padded_vocab(v):
+    return L.load().e2e_padded_vocab(int(v))
+
+
+def ctc_log_softmax(logits, enc_len=None, apply_relu=True, out=None):
+    """logits [U,Tmax,V] (CTC Linear output) -> x [Tmax,U,Vp] frame-major log-posteriors."""
+    _chk(logits, F32, "logits")
+    _chk(enc_len, I32, "enc_len")
+    u, t, v = logits.shape
+    vp = padded_vocab(v)
+    x = out if out is not None else torch.empty((t, u, vp), dtype=F32, device=logits.device)
+    _chk(x, F32, "x", t * u * vp)
+    L.check(L.load().e2e_ctc_log_softmax(L.ptr(logits), u, t, v, L.ptr(enc_len), int(bool(apply_relu)),
+                                        L.ptr(x), vp, _stream()))
+    return x
+
+
+def ctc_init_state(x, enc_len=None, out=None):
+    """x [Tmax,U,Vp] -> r0 [U,Tmax,1,2] (state of the empty prefix)."""
+    _chk(x, F32, "x")
+    _chk(enc_len, I32, "enc_len")
+    t, u, vp = x.shape
+    r0 = out if out is not None else torch.empty((u, t, 1, 2), dtype=F32, device=x.device)
+    _chk(r0, F32, "r0", u * t * 2)
+    L.check(L.load().e2e_ctc_init_state(L.ptr(x), t, u, vp, L.ptr(enc_len), L.ptr(r0), _stream()))
+    return r0
+
+
+def ctc_prefix_score(x, vocab, enc_len, r_prev, prev_lane, last_tok, prefix_len, n_live, cand,
+                     beam, n_cand, flags=0, psi=None, r_out=None, status=None):
+    """One launch of the prefix-score kernel; see e2e_ctc_prefix_score in the header."""
+    t, u, vp = x.shape
+    _chk(x, F32, "x")
+    _chk(enc_len, I32, "enc_len", u)
+    _chk(r_prev, F32, "r_prev")
+    lanes_prev = r_prev.shape[2]
+    if r_prev.shape[0] != u or r_prev.shape[1] != t or r_prev.shape[3] != 2:
+        raise ValueError("r_prev must be [U,Tmax,lanes,2]")
+    n = u * beam
+    _chk(prev_lane, I32, "prev_lane", n)
+    _chk(last_tok, I32, "last_tok", n)
+    _chk(prefix_len, I32, "prefix_len", n)
+    _chk(n_live, I32, "n_live", u)
+    _chk(cand, I32, "cand", n * n_cand)
+    if psi is None:
+        psi = torch.empty((n, n_cand), dtype=F32, device=x.device)
+    if r_out is None:
+        r_out = torch.empty((u, t, beam * n_cand, 2), dtype=F32, device=x.device)
+    _chk(psi, F32, "psi", n * n_cand)
+    _chk(r_out, F32, "r_out", u * t * beam * n_cand * 2)
+    _chk(status, I32, "status", u)
+    L.check(L.load().e2e_ctc_prefix_score(
+        L.ptr(x), t, u, vp, int(vocab), L.ptr(enc_len), L.ptr(r_prev), lanes_prev,
+        L.ptr(prev_lane), L.ptr(last_tok), L.ptr(prefix_len), L.ptr(n_live), L.ptr(cand),
+        int(beam), int(n_cand), int(flags), L.ptr(psi), L.ptr(r_out), L.ptr(status), _stream()))
+    return psi, r_out
+
+
+def beam_candidates(att_logits, n_utts, beam, vocab, n_cand, n_live, att_stats, cand):
+    _chk(att_logits, F32, "att_logits")
+    ld = att_logits.stride(0) if att_logits.dim() == 2 else vocab
+    _chk(n_live, I32, "n_live", n_utts)
+    _chk(att_stats, F32, "att_stats", n_utts * beam * 2)
+    _chk(cand, I32, "cand", n_utts * beam * n_cand)
+    L.check(L.load().e2e_beam_candidates(L.ptr(att_logits), int(ld), int(n_utts), int(beam), int(vocab), int(n_cand),
+                                        L.ptr(n_live), L.ptr(att_stats), L.ptr(cand), _stream()))
+
+
+class BeamBuffers:
+    """Device-resident beam-search bookkeeping for a batch of U utterances
+    (the arrays e2e_beam_combine_prune updates in place)."""
+
+    def __init__(self, n_utts, beam, n_cand, max_steps, min_len, max_len, device, fin_cap=None):
+        u, b = n_utts, beam
+        self.U, self.B, self.C, self.S = u, b, n_cand, max(1, int(max_steps))
+        z = lambda *s, dt=I32: torch.zeros(s, dtype=dt, device=device)
+        self.min_len = min_len.to(device=device, dtype=I32).contiguous()
+        self.max_len = max_len.to(device=device, dtype=I32).contiguous()
+        self.n_live = (self.max_len > 0).to(I32)                 # one empty hypothesis per utterance
+        self.n_active = self.n_live.clone()
+        self.last_tok, self.prefix_len, self.prev_lane = z(u, b), z(u, b), z(u, b)
+        self.score_sum, self.ctc_prob = z(u, b, dt=F32), z(u, b, dt=F32)
+        self.parent_slot = z(u, b)
+        self.hist_tok, self.hist_parent = z(self.S, u, b), z(self.S, u, b)
+        self.hist_score = z(self.S, u, b, dt=F32)
+        self.fin_cap = int(fin_cap if fin_cap is not None else min(b * self.S, 64 + 4 * b))
+        self.fin_count = z(u)
+        self.fin_step, self.fin_parent = z(u, self.fin_cap), z(u, self.fin_cap)
+        self.fin_sum, self.fin_score = z(u, self.fin_cap, dt=F32), z(u, self.fin_cap, dt=F32)
+        self.status = z(u)
+        self.att_stats = z(u * b, 2, dt=F32)
+        self.cand = z(u * b, max(1, n_cand))
+        self.psi = z(u * b, max(1, n_cand), dt=F32)
+
+
+def beam_combine_prune(buf, att_logits, lm_logits, vocab, step, ctc_weight, lm_weight, eos_threshold=1.5):
+    """One decode step of score combine + eos threshold + top-k + prune for all utterances."""
+    _chk(att_logits, F32, "att_logits")
+    _chk(lm_logits, F32, "lm_logits")
+    flags = (L.BEAM_USE_CTC if ctc_weight > 0 else 0) | (L.BEAM_USE_LM if lm_logits is not None else 0)
+    L.check(L.load().e2e_beam_combine_prune(
+        L.ptr(att_logits), int(att_logits.stride(0)), L.ptr(buf.att_stats),
+        L.ptr(lm_logits), int(lm_logits.stride(0)) if lm_logits is not None else 0,
+        L.ptr(buf.cand), L.ptr(buf.psi),
+        buf.U, buf.B, int(vocab), buf.C, int(step),
+        L.ptr(buf.min_len), L.ptr(buf.max_len),
+        float(ctc_weight), float(lm_weight), float(eos_threshold), flags,
+        L.ptr(buf.n_live), L.ptr(buf.n_active), L.ptr(buf.last_tok), L.ptr(buf.prefix_len),
+        L.ptr(buf.score_sum), L.ptr(buf.ctc_prob), L.ptr(buf.prev_lane),
+        L.ptr(buf.parent_slot),
+        L.ptr(buf.hist_tok), L.ptr(buf.hist_parent), L.ptr(buf.hist_score),
+        L.ptr(buf.fin_count), L.ptr(buf.fin_step), L.ptr(buf.fin_parent), L.ptr(buf.fin_sum), L.ptr(buf.fin_score),
+        buf.fin_cap, L.ptr(buf.status), _stream()))
+
+
+def beam_finalize(buf, out_cap=None):
+    """Final N-best: returns (tokens [U,B,cap] i32, scores [U,B,cap] f32, lens [U,B], avg [U,B], n [U])."""
+    dev = buf.n_live.device
+    cap = int(out_cap if out_cap is not None else buf.S + 1)
+    tok = torch.zeros((buf.U, buf.B, cap), dtype=I32, device=dev)
+    sc = torch.zeros((buf.U, buf.B, cap), dtype=F32, device=dev)
+    ln = torch.zeros((buf.U, buf.B), dtype=I32, device=dev)
+    avg = torch.zeros((buf.U, buf.B), dtype=F32, device=dev)
+    n = torch.zeros((buf.U,), dtype=I32, device=dev)
+    L.check(L.load().e2e_beam_finalize(
+        buf.U, buf.B, L.ptr(buf.max_len), L.ptr(buf.n_live), L.ptr(buf.score_sum),
+        L.ptr(buf.hist_tok), L.ptr(buf.hist_parent), L.ptr(buf.hist_score),
+        L.ptr(buf.fin_count), L.ptr(buf.fin_step), L.ptr(buf.fin_parent), L.ptr(buf.fin_sum), L.ptr(buf.fin_score),
+        buf.fin_cap, L.ptr(tok), L.ptr(sc), L.ptr(ln), L.ptr(avg), L.ptr(n), cap, _stream()))
+    return tok, sc, ln, avg, n
+
+
+def launch_count():
+    return int(L.load().e2e_launch_count())

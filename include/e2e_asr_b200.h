@@ -1,0 +1,163 @@
+/*
+ * e2e_asr_b200.h — C ABI of the B200-native joint CTC/attention(+RNNLM)
+ * beam-search decode path (libe2e_asr_b200.so).
+ *
+ * The reference (DanielLin94144/E2E-ASR-Pytorch) is pure Python: it has no FFI
+ * of its own, so each entry point below names the reference code it replaces
+ * (paths relative to the reference root) and INTEGRATION.md shows the ctypes
+ * binding a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller owns every buffer; the library allocates nothing, keeps no
+ *     state between calls except the per-thread error string, and never
+ *     synchronises: all work is enqueued on `stream` (a cudaStream_t);
+ *   - return value: 0 on success, a negative E2E_ERR_* code otherwise
+ *     (e2e_last_error() then describes it).  Nothing throws across the ABI;
+ *   - data-dependent failures of the reference (IndexError / ValueError) are
+ *     reported asynchronously through the `status` words (E2E_STATUS_* bits),
+ *     which the host reads back when it needs the result;
+ *   - "utterance" u in [0,U), beam "slot" b in [0,B), "hypothesis" n = u*B+b,
+ *     "candidate" j in [0,C), prefix-state "lane" l = b*C+j inside an utterance.
+ *
+ * Layouts (all fp32 unless noted)
+ *   x        [Tmax][U][Vp]        frame-major CTC log-posteriors, Vp = e2e_padded_vocab(V)
+ *   r        [U][Tmax][lanes][2]  prefix states: [..][0] non-blank-ending, [..][1] blank-ending
+ *   history  [Smax][U][B]         back-pointers / tokens / per-token scores of every step
+ */
+#ifndef E2E_ASR_B200_H
+#define E2E_ASR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define E2E_ABI_VERSION 1
+
+/* constants of the reference that are part of parity */
+#define E2E_CTC_LOGZERO   (-100000000.0f) /* src/ctc.py:12   */
+#define E2E_CTC_BLANK     0               /* src/ctc.py:13   */
+#define E2E_CTC_EOS       1               /* src/ctc.py:14   */
+#define E2E_DEC_LOG_ZERO  (-10000000.0f)  /* src/decode.py:11 */
+
+/* return codes */
+#define E2E_OK              0
+#define E2E_ERR_ARG        (-1)  /* invalid argument (null pointer, size <= 0, bad alignment, ...) */
+#define E2E_ERR_LAUNCH     (-2)  /* CUDA launch / runtime error (message has the CUDA string)     */
+#define E2E_ERR_UNSUPPORTED (-3) /* size outside what the kernels are built for                   */
+
+/* bits of the per-utterance status words */
+#define E2E_STATUS_PREFIX_TOO_LONG   1 /* len(prefix) > T: reference raises IndexError, src/ctc.py:85          */
+#define E2E_STATUS_TOKEN_NOT_CAND    2 /* beam winner outside the CTC candidates: ValueError, src/decode.py:252 */
+#define E2E_STATUS_FINISHED_OVERFLOW 4 /* more closed hypotheses than the caller's finished-list capacity       */
+
+/* flags of e2e_ctc_prefix_score */
+#define E2E_PREFIX_FULL           1 /* full_compute semantics (src/ctc.py:29-66): candidates are 0..V-1 */
+#define E2E_PREFIX_SKIP_DEAD_ROWS 2 /* do not write state rows t < start (they are never read back by
+                                       the batched beam search; the drop-in scorer always writes them) */
+#define E2E_PREFIX_FAST_MATH      4 /* MUFU ex2/lg2 based log-add-exp instead of expf/log1pf            */
+
+/* flags of e2e_beam_combine_prune */
+#define E2E_BEAM_USE_CTC 1
+#define E2E_BEAM_USE_LM  2
+
+const char *e2e_last_error(void);
+int e2e_abi_version(void);
+/* Row pitch (in floats) of the posterior tensor for a vocabulary of V tokens:
+ * V rounded up to a multiple of 4 so that every row is a 16-byte aligned bulk
+ * copy source. */
+int e2e_padded_vocab(int V);
+
+/* (1) CTC posterior.  Replaces F.log_softmax(self.asr.ctc_layer(enc), dim=-1) minus
+ * the Linear (src/decode.py:94-95; ctc_layer = Linear + ReLU, src/asr.py:29-32):
+ *   x[t][u][v] = log_softmax_v( relu?(logits[u][t][v]) )     t < enc_len[u]
+ * Rows t >= enc_len[u] and pad columns v in [V,Vp) are set to E2E_CTC_LOGZERO.
+ * logits: [U][Tmax][V] row-major (the Linear's output).  enc_len may be NULL (= Tmax). */
+int e2e_ctc_log_softmax(const float *logits, int U, int Tmax, int V, const int *enc_len,
+                        int apply_relu, float *x, int Vp, void *stream);
+
+/* State of the empty prefix.  Replaces CTCPrefixScore.init_state (src/ctc.py:19-27):
+ *   r0[u][t][0][0] = logzero ; r0[u][t][0][1] = sum_{tau<=t} x[tau][u][blank]  (sequential fp32)
+ * r0: [U][Tmax][1][2]. */
+int e2e_ctc_init_state(const float *x, int Tmax, int U, int Vp, const int *enc_len,
+                       float *r0, void *stream);
+
+/* (2) Prefix scores of every (hypothesis, candidate) extension.  Replaces
+ * CTCPrefixScore.cheap_compute (src/ctc.py:68-108) — and .full_compute
+ * (src/ctc.py:29-66) with E2E_PREFIX_FULL — for all live hypotheses of all
+ * utterances in one launch.
+ *   r_prev     [U][Tmax][lanes_prev][2]  states written by the previous step (or r0, lanes_prev=1)
+ *   prev_lane  [U*B]  lane of hypothesis n's own state inside r_prev
+ *   last_tok   [U*B]  last token of hypothesis n's prefix (ignored when prefix_len[n]==0)
+ *   prefix_len [U*B]  len(g) of hypothesis n
+ *   n_live     [U]    live slots per utterance (slots 0..n_live-1); NULL = B everywhere
+ *   cand       [U*B][C] candidate token ids (ignored with E2E_PREFIX_FULL, where C must equal V)
+ *   psi        [U*B][C]            out: prefix log-probabilities
+ *   r_out      [U][Tmax][B*C][2]   out: states of the extended prefixes
+ *   status     [U]                 in/out: OR-ed E2E_STATUS_* bits (may be NULL)
+ */
+int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int V, const int *enc_len,
+                         const float *r_prev, int lanes_prev,
+                         const int *prev_lane, const int *last_tok, const int *prefix_len,
+                         const int *n_live, const int *cand, int B, int C, int flags,
+                         float *psi, float *r_out, int *status, void *stream);
+
+/* (3a) Attention log-softmax statistics + CTC candidate pre-pruning.  Replaces
+ * F.log_softmax(cur_prob) and cur_prob.topk(ctc_beam_size) (src/decode.py:122,129-130).
+ *   att_logits [U*B][ld] decoder outputs (char_trans), row pitch ld >= V
+ *   att_stats  [U*B][2]  out: (max_v logits, log sum_v exp(logits-max)) so that
+ *                        log_softmax(v) = (logits[v]-max) - lse
+ *   cand       [U*B][C]  out: ids of the C largest log-probs, best first (ties: lower id first);
+ *                        C may be 0 (no CTC) in which case only the statistics are produced */
+int e2e_beam_candidates(const float *att_logits, int ld, int U, int B, int V, int C,
+                        const int *n_live, float *att_stats, int *cand, void *stream);
+
+/* (3b) Score combine + <eos> threshold + top-k + length-normalised prune of one decode
+ * step for every utterance.  Replaces src/decode.py:134-177 and Hypothesis.addTopk /
+ * avgScore (src/decode.py:214-263).
+ * Beam state (updated IN PLACE, all [U][B] unless noted):
+ *   n_live [U], last_tok, prefix_len, score_sum (sequential fp32 sum of token scores),
+ *   ctc_prob (psi of the hypothesis), prev_lane;
+ *   n_active [U] (may be NULL) receives n_live for utterances that still have a step to run
+ *   and 0 for the others — it is the `n_live` argument of the NEXT step's (2)/(3a) calls
+ * Per-step outputs:
+ *   parent_slot [U][B]  slot of each new hypothesis' parent (identity for idle utterances) — the
+ *                       caller gathers decoder / LM / attention states with it
+ *   hist_tok, hist_parent (int32) and hist_score (fp32): row `step` of [Smax][U][B]
+ * Closed (<eos>-terminated) hypotheses are appended per utterance:
+ *   fin_count [U]; fin_step, fin_parent (int32), fin_sum, fin_score (fp32): [U][fin_cap]
+ * Utterances with step >= max_len[u] are left untouched.
+ *   lm_logits may be NULL iff E2E_BEAM_USE_LM is clear; cand/psi iff E2E_BEAM_USE_CTC is clear. */
+int e2e_beam_combine_prune(const float *att_logits, int ld_att, const float *att_stats,
+                           const float *lm_logits, int ld_lm,
+                           const int *cand, const float *psi,
+                           int U, int B, int V, int C, int step,
+                           const int *min_len, const int *max_len,
+                           float ctc_weight, float lm_weight, float eos_threshold, int flags,
+                           int *n_live, int *n_active, int *last_tok, int *prefix_len,
+                           float *score_sum, float *ctc_prob, int *prev_lane,
+                           int *parent_slot,
+                           int *hist_tok, int *hist_parent, float *hist_score,
+                           int *fin_count, int *fin_step, int *fin_parent, float *fin_sum, float *fin_score,
+                           int fin_cap, int *status, void *stream);
+
+/* Final N-best selection + back-tracking.  Replaces src/decode.py:180-183 and
+ * Hypothesis.outIndex (src/decode.py:279-281): closed hypotheses followed by the last
+ * beam, stable-sorted by mean token score, best B kept.
+ *   out_tok, out_score [U][B][out_cap]; out_len, out_avg [U][B]; out_n [U] */
+int e2e_beam_finalize(int U, int B, const int *max_len,
+                      const int *n_live, const float *score_sum,
+                      const int *hist_tok, const int *hist_parent, const float *hist_score,
+                      const int *fin_count, const int *fin_step, const int *fin_parent,
+                      const float *fin_sum, const float *fin_score, int fin_cap,
+                      int *out_tok, float *out_score, int *out_len, float *out_avg, int *out_n,
+                      int out_cap, void *stream);
+
+/* Number of kernel launches issued through this library by the calling process
+ * (for bench.py's gpu_launches claim). */
+long long e2e_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E2E_ASR_B200_H */

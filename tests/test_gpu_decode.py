@@ -1,0 +1,146 @@
+"""End-to-end parity on the B200: batched device beam search (BeamDecoder.decode_batch) vs the
+per-hypothesis CPU oracle (oracle/beam_oracle.py, itself pinned to the live reference) on
+identical random-init weights and seeded synthetic features.
+
+north_star: 1-best token sequences identical except for documented score ties.  The acoustic
+model / LM run in fp32 on both sides but through different libraries (cuBLAS/cuDNN vs CPU
+kernels), so per-token scores agree to ~1e-5; a differing sequence is accepted only if the
+oracle's own scores of the two sequences are closer than TIE_TOL (a tie at fp32 resolution).
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 2e-4    # |mean score| agreement for identical sequences
+TIE_TOL = 5e-4      # score gap below which two hypotheses count as tied
+
+
+def _models(vocab=31, peak=4.0):
+    from e2e_asr_pytorch_b200 import synth
+    asr = synth.build_asr(vocab, synth.TINY_ASR_CFG, seed=0, peak=peak)
+    lm = synth.build_lm(vocab, synth.TINY_LM_CFG, seed=1)
+    tmp = tempfile.mkdtemp()
+    torch.save({"model": lm.state_dict()}, os.path.join(tmp, "lm.pth"))
+    yaml.safe_dump({"model": synth.TINY_LM_CFG}, open(os.path.join(tmp, "lm.yaml"), "w"))
+    return asr, lm, os.path.join(tmp, "lm.pth"), os.path.join(tmp, "lm.yaml")
+
+
+def _oracle_nbest(asr, lm, feat, n, beam, lm_w, ctc_w, max_ratio=0.2):
+    from oracle import beam_oracle as BO
+    with torch.no_grad():
+        nb = BO.decode_utterance(asr, feat[None, :n], torch.LongTensor([n]), beam, 0.01, max_ratio,
+                                 lm=lm if lm_w > 0 else None, lm_weight=lm_w, ctc_weight=ctc_w)
+    return BO.nbest_as_arrays(nb)
+
+
+def _compare(dev_nbest, ora_nbest, what):
+    """Returns (#identical 1-best, #ties) and asserts everything else."""
+    same = ties = 0
+    d0, o0 = dev_nbest[0], ora_nbest[0]
+    if d0.outIndex == o0[0].tolist():
+        same = 1
+        assert abs(float(d0.avgScore()) - float(o0[2])) < SCORE_TOL, what
+        assert np.allclose(np.array([float(s) for s in d0.output_scores]), o0[1], atol=2e-3), what
+    else:
+        # tie audit: the device's 1-best must be in the oracle's N-best with a score within TIE_TOL of the oracle's best
+        cands = [o for o in ora_nbest if o[0].tolist() == d0.outIndex]
+        assert cands, what + ": device 1-best %s not in the oracle N-best" % d0.outIndex[:10]
+        assert abs(float(cands[0][2]) - float(o0[2])) < TIE_TOL, what + ": not a tie"
+        ties = 1
+    return same, ties
+
+
+@pytest.mark.parametrize("beam,lm_w", [(2, 0.0), (8, 0.5), (4, 0.3)])
+def test_decode_batch_matches_oracle(cuda, beam, lm_w):
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth
+    asr, lm, lm_path, lm_cfg = _models()
+    lens = [64, 120, 92, 200, 76, 148]
+    ids = list(range(len(lens)))
+    feat, fl = synth.padded_batch(ids, lens)
+    dec = BeamDecoder(asr, None, beam, 0.01, 0.2, lm_path=lm_path, lm_config=lm_cfg, lm_weight=lm_w, ctc_weight=0.5).to(cuda)
+    out = dec.decode_batch(feat.to(cuda), fl.to(cuda))
+    assert len(out) == len(lens)
+    same = ties = 0
+    for k, n in enumerate(lens):
+        ora = _oracle_nbest(asr, lm, feat[k], n, beam, lm_w, 0.5)
+        assert len(out[k]) == len(ora)
+        s, t = _compare(out[k], ora, "beam %d lm %.1f utt %d" % (beam, lm_w, k))
+        same, ties = same + s, ties + t
+    print("beam %d lm_w %.1f: identical 1-best %d/%d, ties %d" % (beam, lm_w, same, len(lens), ties))
+    assert same >= len(lens) - 1
+    # strict drop-in call: one utterance, batch dimension 1 (decode.py:65-67)
+    one = dec(feat[1:2, :lens[1]].to(cuda), fl[1:2].to(cuda))
+    assert [h.outIndex for h in one] == [h.outIndex for h in out[1]]
+    with pytest.raises(AssertionError):
+        dec(feat[:2].to(cuda), fl[:2].to(cuda))
+
+
+def test_decode_without_ctc_and_without_lm(cuda):
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth
+    asr, lm, lm_path, lm_cfg = _models()
+    lens = [64, 100]
+    feat, fl = synth.padded_batch([0, 1], lens)
+    for lm_w in (0.0, 0.5):
+        dec = BeamDecoder(asr, None, 4, 0.01, 0.2, lm_path=lm_path, lm_config=lm_cfg, lm_weight=lm_w, ctc_weight=0.0).to(cuda)
+        out = dec.decode_batch(feat.to(cuda), fl.to(cuda))
+        for k, n in enumerate(lens):
+            ora = _oracle_nbest(asr, lm, feat[k], n, 4, lm_w, 0.0)
+            _compare(out[k], ora, "no-ctc lm %.1f utt %d" % (lm_w, k))
+
+
+def test_decode_eos_termination(cuda):
+    """Bias the speller towards <eos> so the threshold branch (decode.py:232-241) and the
+    closed-hypothesis bookkeeping run; random-init weights alone never close a hypothesis."""
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth
+    asr, lm, lm_path, lm_cfg = _models()
+    with torch.no_grad():
+        asr.decoder.char_trans.bias[1] += 6.0
+    lens = [64, 120, 92]
+    feat, fl = synth.padded_batch([0, 1, 2], lens)
+    dec = BeamDecoder(asr, None, 4, 0.01, 0.2, lm_path=lm_path, lm_config=lm_cfg, lm_weight=0.3, ctc_weight=0.5).to(cuda)
+    out = dec.decode_batch(feat.to(cuda), fl.to(cuda))
+    closed = 0
+    for k, n in enumerate(lens):
+        ora = _oracle_nbest(asr, lm, feat[k], n, 4, 0.3, 0.5)
+        assert [len(h.outIndex) for h in out[k]] == [len(o[0]) for o in ora]
+        _compare(out[k], ora, "eos utt %d" % k)
+        closed += sum(1 for o in ora if len(o[0]) < int(np.ceil(n * 0.2)))
+    assert closed > 0, "the fixture did not exercise <eos> termination"
+
+
+def test_decode_crash_envelope_is_reported(cuda):
+    """ceil(L*max_len_ratio) > T_enc: every candidate's psi becomes log-zero and the reference
+    dies with ValueError (decode.py:252) or IndexError (ctc.py:85) — SURVEY.md §7.2-4."""
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth
+    asr, _, _, _ = _models()
+    feat, fl = synth.padded_batch([0], [64])
+    dec = BeamDecoder(asr, None, 2, 0.01, 0.5, ctc_weight=0.5).to(cuda)     # 32 steps > T_enc = 16
+    with pytest.raises((ValueError, IndexError)):
+        dec.decode_batch(feat.to(cuda), fl.to(cuda))
+
+
+def test_golden_nbest_from_reference(cuda):
+    """Fixtures generated by tools/make_golden.py from the UNMODIFIED reference BeamDecoder."""
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth
+    path = os.path.join(os.path.dirname(__file__), "golden", "beam_nbest_tiny.npz")
+    gold = np.load(path, allow_pickle=False)
+    asr, lm, lm_path, lm_cfg = _models()
+    same = total = 0
+    for case in range(int(gold["n_cases"])):
+        beam, lm_w, uid, n = (gold["case%d_%s" % (case, k)].item() for k in ("beam", "lm_w", "utt", "len"))
+        feat = synth.utterance(int(uid), int(n))
+        dec = BeamDecoder(asr, None, int(beam), 0.01, 0.2, lm_path=lm_path, lm_config=lm_cfg,
+                          lm_weight=float(lm_w), ctc_weight=0.5).to(cuda)
+        out = dec(feat[None].to(cuda), torch.LongTensor([int(n)]).to(cuda))
+        ora = []
+        for k in range(int(gold["case%d_nbest" % case])):
+            ora.append((gold["case%d_tok%d" % (case, k)], gold["case%d_sc%d" % (case, k)], gold["case%d_avg%d" % (case, k)]))
+        s, _ = _compare(out, ora, "golden case %d" % case)
+        same, total = same + s, total + 1
+    assert same >= total - 1

@@ -1,0 +1,236 @@
+"""Kernel-level parity on the B200: CUDA path (through the C ABI) vs the CPU oracle.
+
+Tolerances: posteriors 2e-6 abs (fp32 log-softmax); prefix scores / states 1e-4 abs or
+2 ulp, whichever is larger (tests/_util.prefix_tolerance); integer outputs exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests._util import posteriors, assert_prefix_close, LOGZERO
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from e2e_asr_pytorch_b200 import ops, _lib
+    return ops, _lib
+
+
+# ----------------------------------------------------------------------------------------------
+# (1) CTC posterior + empty-prefix state
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_utts,t_max,vocab", [(3, 17, 31), (2, 9, 5), (4, 33, 200), (2, 6, 10000), (1, 1, 31)])
+def test_ctc_log_softmax_matches_torch(cuda, n_utts, t_max, vocab):
+    ops, _ = _ops()
+    from oracle import ctc_prefix_oracle as O
+    g = torch.Generator().manual_seed(vocab + t_max)
+    logits = torch.randn(n_utts, t_max, vocab, generator=g) * 3
+    enc_len = torch.tensor([max(1, t_max - 2 * i) for i in range(n_utts)], dtype=torch.int32)
+    x = ops.ctc_log_softmax(logits.to(cuda), enc_len.to(cuda), apply_relu=True).cpu()
+    vp = x.shape[-1]
+    assert x.shape == (t_max, n_utts, vp) and vp % 4 == 0 and vp >= vocab
+    ref = torch.log_softmax(torch.relu(logits), dim=-1)                       # decode.py:94-95 on the CPU
+    for u in range(n_utts):
+        n = int(enc_len[u])
+        assert torch.allclose(x[:n, u, :vocab], ref[u, :n], atol=2e-6, rtol=0), (x[:n, u, :vocab] - ref[u, :n]).abs().max()
+        assert (x[n:, u] == LOGZERO).all() and (x[:, u, vocab:] == LOGZERO).all()
+    r0 = ops.ctc_init_state(x.to(cuda), enc_len.to(cuda)).cpu().numpy()
+    for u in range(n_utts):
+        n = int(enc_len[u])
+        want = O.blank_state(x[:n, u, :vocab].numpy())                         # same device posteriors -> bit exact
+        assert np.array_equal(r0[u, :n, 0], want)
+
+
+def test_ctc_log_softmax_without_relu(cuda):
+    ops, _ = _ops()
+    logits = torch.randn(2, 5, 31, generator=torch.Generator().manual_seed(3))
+    x = ops.ctc_log_softmax(logits.to(cuda), None, apply_relu=False).cpu()
+    assert torch.allclose(x[:, :, :31].transpose(0, 1), torch.log_softmax(logits, -1), atol=2e-6, rtol=0)
+
+
+# ----------------------------------------------------------------------------------------------
+# (2) prefix score: a beam-search-shaped chain of steps against the oracle
+# ----------------------------------------------------------------------------------------------
+def _chain(cuda, rng, n_utts, t_lens, vocab, beam, n_cand, n_steps, flags=0, check_states=True):
+    ops, L = _ops()
+    from oracle import c_oracle as CO
+    t_max = max(t_lens)
+    post = posteriors(rng, n_utts, t_max, vocab)                               # [U,T,V]
+    vp = ops.padded_vocab(vocab)
+    x = np.full((t_max, n_utts, vp), LOGZERO, np.float32)
+    x[:, :, :vocab] = post.transpose(1, 0, 2)
+    for u, n in enumerate(t_lens):
+        x[n:, u] = LOGZERO
+    xd = torch.from_numpy(x).to(cuda)
+    enc_len = torch.tensor(t_lens, dtype=torch.int32, device=cuda)
+    r_prev_d = ops.ctc_init_state(xd, enc_len)
+    # oracle-side beams: per utterance a list of (prefix, state[T,2])
+    beams = [[([], CO.blank_state(post[u, :t_lens[u]]))] for u in range(n_utts)]
+    prev_lane = torch.zeros(n_utts * beam, dtype=torch.int32)
+    status = torch.zeros(n_utts, dtype=torch.int32, device=cuda)
+    worst = 0.0
+    r_bufs = [torch.empty((n_utts, t_max, beam * n_cand, 2), device=cuda) for _ in range(2)]
+    for step in range(n_steps):
+        n_live = torch.tensor([len(b) for b in beams], dtype=torch.int32)
+        cand = np.zeros((n_utts, beam, n_cand), np.int32)
+        last = np.zeros((n_utts, beam), np.int32)
+        plen = np.zeros((n_utts, beam), np.int32)
+        for u in range(n_utts):
+            for b, (g, _) in enumerate(beams[u]):
+                cs = rng.permutation(vocab)[:n_cand].astype(np.int32)
+                if (step + b) % 2 == 0 and 1 not in cs:
+                    cs[int(rng.integers(n_cand))] = 1                          # exercise the <eos> override
+                if g and (step + b) % 3 == 0 and g[-1] not in cs:
+                    cs[int(rng.integers(n_cand))] = g[-1]                      # exercise the repeated-token column
+                if len(set(cs.tolist())) < n_cand:
+                    cs = rng.permutation(vocab)[:n_cand].astype(np.int32)
+                cand[u, b], last[u, b], plen[u, b] = cs, (g[-1] if g else 0), len(g)
+        r_out = r_bufs[step % 2]
+        r_out.fill_(float("nan"))
+        psi, _ = ops.ctc_prefix_score(xd, vocab, enc_len, r_prev_d, prev_lane.to(cuda),
+                                      torch.from_numpy(last.reshape(-1)).to(cuda), torch.from_numpy(plen.reshape(-1)).to(cuda),
+                                      n_live.to(cuda), torch.from_numpy(cand.reshape(-1, n_cand)).to(cuda),
+                                      beam, n_cand, flags, r_out=r_out, status=status)
+        psi = psi.cpu().numpy().reshape(n_utts, beam, n_cand)
+        r_host = r_out.cpu().numpy().reshape(n_utts, t_max, beam, n_cand, 2) if check_states else None
+        new_beams, new_lane = [], np.zeros((n_utts, beam), np.int32)
+        for u in range(n_utts):
+            n = t_lens[u]
+            outs = []
+            for b, (g, st) in enumerate(beams[u]):
+                p_o, r_o = CO.extend(post[u, :n], len(g), g[-1] if g else 0, st, cand[u, b].tolist())
+                worst = max(worst, assert_prefix_close(psi[u, b], p_o, "psi step %d utt %d slot %d" % (step, u, b)))
+                if check_states:
+                    got = r_host[u, :n, b].transpose(1, 0, 2)                  # [C,T,2]
+                    if flags & L.PREFIX_SKIP_DEAD_ROWS:
+                        first = max(1, len(g))
+                        got, r_cmp = got[:, first:], r_o[:, first:]
+                    else:
+                        r_cmp = r_o
+                    worst = max(worst, assert_prefix_close(got, r_cmp, "r step %d utt %d slot %d" % (step, u, b)))
+                outs.append((g, r_o))
+            # survivors: random (parent, candidate) pairs, at most `beam`
+            picks = [(b, j) for b in range(len(outs)) for j in range(n_cand)]
+            keep = [picks[i] for i in rng.permutation(len(picks))[:beam]]
+            nb = []
+            for k, (b, j) in enumerate(keep):
+                g, r_o = outs[b]
+                nb.append((g + [int(cand[u, b, j])], np.ascontiguousarray(r_o[j])))
+                new_lane[u, k] = b * n_cand + j
+            new_beams.append(nb)
+        beams, prev_lane, r_prev_d = new_beams, torch.from_numpy(new_lane.reshape(-1)), r_out
+    assert int(status.abs().sum()) == 0
+    return worst
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_prefix_score_cfg1_shape(cuda, fast):
+    _, L = _ops()
+    rng = np.random.default_rng(11)
+    w = _chain(cuda, rng, n_utts=3, t_lens=[250, 249, 100], vocab=31, beam=2, n_cand=3, n_steps=12,
+               flags=L.PREFIX_FAST_MATH if fast else 0)
+    print("cfg1-shape chain: max |gpu-oracle| = %.3g (fast=%s)" % (w, fast))
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_prefix_score_cfg2_shape(cuda, fast):
+    _, L = _ops()
+    rng = np.random.default_rng(12)
+    w = _chain(cuda, rng, n_utts=5, t_lens=[180, 37, 96, 64, 181], vocab=31, beam=8, n_cand=12, n_steps=20,
+               flags=L.PREFIX_FAST_MATH if fast else 0)
+    print("cfg2-shape chain: max |gpu-oracle| = %.3g (fast=%s)" % (w, fast))
+
+
+def test_prefix_score_skip_dead_rows(cuda):
+    _, L = _ops()
+    rng = np.random.default_rng(13)
+    _chain(cuda, rng, n_utts=2, t_lens=[70, 33], vocab=31, beam=4, n_cand=6, n_steps=30, flags=L.PREFIX_SKIP_DEAD_ROWS)
+
+
+def test_prefix_score_longform_beam16(cuda):
+    rng = np.random.default_rng(14)
+    w = _chain(cuda, rng, n_utts=2, t_lens=[875, 640], vocab=31, beam=16, n_cand=24, n_steps=6)
+    print("cfg4-shape chain: max |gpu-oracle| = %.3g" % w)
+
+
+def test_prefix_score_large_vocab_gather(cuda):
+    rng = np.random.default_rng(15)
+    w = _chain(cuda, rng, n_utts=2, t_lens=[60, 45], vocab=10000, beam=8, n_cand=12, n_steps=6)
+    print("cfg3-shape chain (gather variant): max |gpu-oracle| = %.3g" % w)
+
+
+def test_prefix_score_midsize_vocab_rows(cuda):
+    rng = np.random.default_rng(16)
+    _chain(cuda, rng, n_utts=2, t_lens=[50, 41], vocab=200, beam=3, n_cand=4, n_steps=5)
+
+
+# ----------------------------------------------------------------------------------------------
+# drop-in CTCPrefixScore class (src/ctc.py interface)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("t_len,vocab,n_cand", [(1, 31, 3), (2, 31, 3), (7, 31, 12), (60, 31, 12), (50, 200, 12)])
+def test_dropin_scorer_against_oracle(cuda, t_len, vocab, n_cand):
+    from e2e_asr_pytorch_b200 import CTCPrefixScore
+    from oracle import ctc_prefix_oracle as O
+    rng = np.random.default_rng(100 + t_len)
+    post = posteriors(rng, 1, t_len, vocab)
+    dev = CTCPrefixScore(torch.from_numpy(post).to(cuda))
+    ora = O.PrefixScorerOracle(post)
+    assert (dev.logzero, dev.blank, dev.eos, dev.odim, dev.input_length) == (ora.logzero, ora.blank, ora.eos, ora.odim, ora.input_length)
+    assert np.array_equal(dev.x, ora.x)
+    r_dev, r_ora = dev.init_state(), ora.init_state()
+    assert isinstance(r_dev, np.ndarray) and r_dev.shape == (t_len, 2) and np.array_equal(r_dev, r_ora)
+    g = []
+    for step in range(min(t_len + 2, 10)):
+        cs = [int(c) for c in rng.permutation(vocab)[:n_cand]]
+        if step % 2 == 0 and 1 not in cs:
+            cs[0] = 1
+        if g and step % 3 == 0 and g[-1] not in cs:
+            cs[-1] = g[-1]
+        try:
+            p_o, s_o = ora.cheap_compute(g, r_ora, cs)
+        except IndexError:
+            with pytest.raises(IndexError):
+                dev.cheap_compute(g, r_dev, cs)
+            break
+        p_d, s_d = dev.cheap_compute(g, r_dev, cs)
+        assert p_d.shape == (n_cand,) and s_d.shape == (n_cand, t_len, 2) and p_d.dtype == np.float32
+        assert_prefix_close(p_d, p_o, "cheap psi")
+        assert_prefix_close(s_d, s_o, "cheap r")
+        pf_o, sf_o = ora.full_compute(g, r_ora)
+        pf_d, sf_d = dev.full_compute(g, r_dev)
+        assert pf_d.shape == (vocab,) and sf_d.shape == (vocab, t_len, 2)
+        assert_prefix_close(pf_d, pf_o, "full psi")
+        assert_prefix_close(sf_d, sf_o, "full r")
+        k = int(rng.integers(n_cand))
+        g = g + [cs[k]]
+        r_dev, r_ora = s_d[k], s_o[k]
+
+
+def test_dropin_scorer_device_state_and_errors(cuda):
+    from e2e_asr_pytorch_b200 import CTCPrefixScore, _lib
+    post = posteriors(np.random.default_rng(5), 1, 20, 31)
+    sc = CTCPrefixScore(torch.from_numpy(post).to(cuda), device_state=True)
+    r0 = sc.init_state()
+    psi, r = sc.cheap_compute([], r0, [1, 2, 3])
+    assert psi.is_cuda and r.is_cuda and tuple(r.shape) == (3, 20, 2)
+    psi2, _ = sc.cheap_compute([2], r[1], [1, 2, 5])
+    assert torch.isfinite(psi2).all()
+    with pytest.raises(_lib.E2EError):
+        CTCPrefixScore(torch.from_numpy(post))                                  # CPU tensor: no fallback
+
+
+def test_prefix_too_long_sets_status(cuda):
+    ops, L = _ops()
+    post = posteriors(np.random.default_rng(6), 1, 4, 31)
+    x = np.full((4, 1, 32), LOGZERO, np.float32)
+    x[:, 0, :31] = post[0]
+    xd = torch.from_numpy(x).to(cuda)
+    enc_len = torch.tensor([4], dtype=torch.int32, device=cuda)
+    r0 = ops.ctc_init_state(xd, enc_len)
+    status = torch.zeros(1, dtype=torch.int32, device=cuda)
+    z = torch.zeros(1, dtype=torch.int32, device=cuda)
+    ops.ctc_prefix_score(xd, 31, enc_len, r0, z, z, torch.tensor([6], dtype=torch.int32, device=cuda),
+                         torch.ones(1, dtype=torch.int32, device=cuda),
+                         torch.tensor([[1, 2, 3]], dtype=torch.int32, device=cuda), 1, 3, 0, status=status)
+    assert int(status[0]) & L.STATUS_PREFIX_TOO_LONG

@@ -1,0 +1,148 @@
+"""Host-side logic on the CPU: drop-in interface surface, batched stepper vs the per-hypothesis
+module protocol, utterance sharding and the N-best all-gather (gloo, world_size 2)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_beam_decoder_constructor_surface(tmp_path):
+    import yaml
+    from e2e_asr_pytorch_b200 import BeamDecoder, Hypothesis, synth
+    asr = synth.build_asr(31, synth.TINY_ASR_CFG)
+    lm = synth.build_lm(31, synth.TINY_LM_CFG)
+    torch.save({"model": lm.state_dict()}, str(tmp_path / "lm.pth"))
+    yaml.safe_dump({"model": synth.TINY_LM_CFG}, open(str(tmp_path / "lm.yaml"), "w"))
+    dec = BeamDecoder(asr, None, 8, 0.01, 0.2, lm_path=str(tmp_path / "lm.pth"), lm_config=str(tmp_path / "lm.yaml"),
+                      lm_weight=0.5, ctc_weight=0.5)
+    assert (dec.beam_size, dec.min_len_ratio, dec.max_len_ratio) == (8, 0.01, 0.2)
+    assert dec.apply_ctc and dec.ctc_w == 0.5 and dec.ctc_beam_size == 12        # int(1.5*8), decode.py:34
+    assert dec.apply_lm and dec.lm_w == 0.5 and not dec.apply_emb
+    msg = dec.create_msg()
+    assert msg[0].startswith("Decode spec| Beam size = 8") and len(msg) == 3
+    for k, v in lm.state_dict().items():
+        assert torch.equal(dec.lm.state_dict()[k], v)
+    import copy, pickle
+    pickle.loads(pickle.dumps(copy.deepcopy(dec)))                                # bin/test_asr.py:108,138 deep-copies + pickles
+    with pytest.raises(AssertionError):                                           # decode.py:32
+        asr2 = synth.build_asr(31, dict(synth.TINY_ASR_CFG, ctc_weight=0.0))
+        BeamDecoder(asr2, None, 2, 0.01, 0.2, ctc_weight=0.5)
+    h = Hypothesis([5, 6, 1], [-1.0, -2.0, -3.0], -2.0)
+    assert h.outIndex == [5, 6, 1] and float(h.avgScore()) == -2.0 and len(h.output_scores) == 3
+
+
+def test_batched_stepper_matches_per_hypothesis_modules():
+    from e2e_asr_pytorch_b200 import synth
+    from e2e_asr_pytorch_b200.stepper import BatchedStepper
+    asr = synth.build_asr(31, synth.TINY_ASR_CFG, seed=0, peak=4.0)
+    lm = synth.build_lm(31, synth.TINY_LM_CFG, seed=1)
+    lens, beam = [64, 120, 92], 3
+    feat, fl = synth.padded_batch([3, 4, 5], lens)
+    with torch.no_grad():
+        st = BatchedStepper(asr, lm)
+        enc, enc_len = st.encode(feat, fl)
+        st.start(enc, enc_len, beam)
+        a1, l1 = st.step(torch.zeros(len(lens) * beam, dtype=torch.long))
+        st.reorder(torch.zeros((len(lens), beam), dtype=torch.int32))
+        toks = [5, 7, 9]
+        a2, l2 = st.step(torch.tensor(toks * len(lens)))
+        for u, n in enumerate(lens):
+            e, el = asr.encoder(feat[u:u + 1, :n], fl[u:u + 1])                  # exact batch-1 encode
+            assert torch.allclose(e[0], enc[u, :int(el)], atol=2e-6)
+            asr.attention.reset_mem()
+            asr.set_state(asr.decoder.init_state(1), None)
+            _, ctx = asr.attention(asr.decoder.get_query(), e, el)
+            lg, _ = asr.decoder(torch.cat([asr.pre_embed(torch.LongTensor([0])), ctx], -1))
+            lmo, lmh = lm(torch.LongTensor([[0]]), torch.ones([1]), hidden=None)
+            assert torch.allclose(lg[0], a1[u * beam], atol=2e-6) and torch.allclose(lmo[0, 0], l1[u * beam], atol=2e-6)
+            dstate, pa = asr.decoder.get_state(), asr.attention.att_layer.prev_att
+            for b, tk in enumerate(toks):
+                asr.set_state(dstate, pa)
+                _, ctx2 = asr.attention(asr.decoder.get_query(), e, el)
+                lg2, _ = asr.decoder(torch.cat([asr.pre_embed(torch.LongTensor([tk])), ctx2], -1))
+                lmo2, _ = lm(torch.LongTensor([[tk]]), torch.ones([1]), hidden=lmh)
+                assert torch.allclose(lg2[0], a2[u * beam + b], atol=3e-6)
+                assert torch.allclose(lmo2[0, 0], l2[u * beam + b], atol=3e-6)
+
+
+def test_shard_plan_is_balanced_and_complete():
+    from e2e_asr_pytorch_b200 import shard, synth
+    lengths = synth.devclean_lengths(2620)
+    assert lengths.min() >= 150 and lengths.max() <= 3300 and np.all(lengths % 4 == 0)
+    for world in (1, 2, 4, 8):
+        parts = shard.plan_shards(lengths, world)
+        allidx = np.sort(np.concatenate(parts))
+        assert np.array_equal(allidx, np.arange(len(lengths)))
+        cost = [shard.utterance_cost(lengths[p]).sum() for p in parts]
+        assert max(cost) / (sum(cost) / world) < 1.01
+    batches = shard.make_batches(np.arange(100), lengths[:100], max_utts=16)
+    assert sorted(sum(batches, [])) == list(range(100)) and all(len(b) <= 16 for b in batches)
+    firsts = [lengths[b[0]] for b in batches]
+    assert firsts == sorted(firsts, reverse=True)
+
+
+def _fake_decode(lengths, beam, ratio):
+    def fn(batch):
+        n = len(batch)
+        cap = int(np.ceil(max(lengths[i] for i in batch) * ratio)) + 1
+        tok = torch.zeros((n, beam, cap), dtype=torch.int32)
+        sc = torch.zeros((n, beam, cap))
+        ln = torch.zeros((n, beam), dtype=torch.int32)
+        avg = torch.zeros((n, beam))
+        for k, i in enumerate(batch):
+            m = int(np.ceil(lengths[i] * ratio))
+            for b in range(beam):
+                tok[k, b, :m] = torch.arange(m, dtype=torch.int32) + 100 * i + b
+                sc[k, b, :m] = -0.5 * (b + 1) - 1e-3 * i
+                ln[k, b], avg[k, b] = m, -0.5 * (b + 1) - 1e-3 * i
+        return tok, sc, ln, avg, torch.full((n,), beam, dtype=torch.int32)
+    return fn
+
+
+def test_pack_unpack_roundtrip_single_rank():
+    from e2e_asr_pytorch_b200 import shard
+    lengths = np.array([40, 80, 64, 120, 44])
+    tok, sc, ln, avg, n = shard.decode_sharded(_fake_decode(lengths, 3, 0.2), lengths, 3, 0.2, max_utts=2)
+    want = _fake_decode(lengths, 3, 0.2)(list(range(5)))
+    assert torch.equal(tok, want[0]) and torch.equal(sc, want[1]) and torch.equal(ln, want[2])
+    assert torch.equal(avg, want[3]) and torch.equal(n, want[4])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from e2e_asr_pytorch_b200 import shard
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    lengths = np.array([40, 80, 64, 120, 44, 200, 52, 96, 100])
+    res = shard.decode_sharded(_fake_decode(lengths, 3, 0.2), lengths, 3, 0.2, rank=rank, world_size=world, max_utts=2)
+    torch.save(res, os.path.join(out_dir, "rank%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_decode_allgather_gloo_world2(tmp_path):
+    """N>1 path on the CPU: two gloo ranks decode disjoint shards, one all-gather, and every
+    rank ends with the single-rank result in utterance order."""
+    import torch.multiprocessing as mp
+    from e2e_asr_pytorch_b200 import shard
+    port = _free_port()
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    lengths = np.array([40, 80, 64, 120, 44, 200, 52, 96, 100])
+    want = shard.decode_sharded(_fake_decode(lengths, 3, 0.2), lengths, 3, 0.2)
+    for r in range(2):
+        got = torch.load(str(tmp_path / ("rank%d.pt" % r)))
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
