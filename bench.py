@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — beam-8 + RNNLM joint CTC/attention decode throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1]): char (31-token) VGG+BLSTM CTC-attention model with
+librispeech_asr.yaml dims + random-init 4x1024 RNNLM, beam 8, ctc_weight 0.5, lm_weight 0.5,
+2620 synthetic utterances with a dev-clean-like length distribution per GPU (weak scaling:
+N GPUs decode N x 2620 utterances, sharded by utterance, one all-gather of the N-best).
+A "step" is one pass of the hot path over that whole set.
+
+Prints ONE JSON line (rank 0).  ``value`` = utterances/s with the features already resident in
+HBM; ``e2e`` = the same through BeamDecoder.decode_batch with pinned HOST features (H2D inside
+the timed region, N-best read back to the host).  ``roofline`` describes the prefix-score
+kernel (the dominant hand-written kernel), timed live with CUDA events around every launch.
+``--impl reference`` times the CPU implementation (oracle port of the reference — the reference
+itself is Python under /root/reference and cannot travel to the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BEAM, CTC_W, LM_W, MIN_RATIO, MAX_RATIO, VOCAB = 8, 0.5, 0.5, 0.01, 0.2, 31
+N_UTTS = 2620
+METRIC = "beam-8+LM joint CTC/attn decode utts/sec"
+
+
+def load_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def workload_lengths(world):
+    from e2e_asr_pytorch_b200 import synth
+    # replica r uses the same length distribution with its own seed (cfg5: "8 x 2620 utts")
+    return np.concatenate([synth.devclean_lengths(N_UTTS, seed=2 + r) for r in range(world)])
+
+
+def build_models(device):
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth
+    import tempfile
+    import yaml
+    asr = synth.build_asr(VOCAB, seed=0)
+    lm = synth.build_lm(VOCAB, seed=1)
+    tmp = tempfile.mkdtemp(prefix="e2e_bench_")
+    torch.save({"model": lm.state_dict()}, os.path.join(tmp, "lm.pth"))
+    yaml.safe_dump({"model": synth.LM_MODEL_CFG}, open(os.path.join(tmp, "lm.yaml"), "w"))
+    dec = BeamDecoder(asr, None, BEAM, MIN_RATIO, MAX_RATIO, lm_path=os.path.join(tmp, "lm.pth"),
+                      lm_config=os.path.join(tmp, "lm.yaml"), lm_weight=LM_W, ctc_weight=CTC_W)
+    if device is not None:
+        dec = dec.to(device)
+    return dec, asr, lm
+
+
+def make_features(ids, lengths, pin):
+    """Host features of the utterances ``ids`` (seeded per utterance), zero padded."""
+    from e2e_asr_pytorch_b200 import synth
+    return synth.padded_batch(ids, [lengths[i] for i in ids], pin=pin)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from e2e_asr_pytorch_b200 import shard, ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world)
+    assert torch.cuda.is_available(), "the B200 arm has no CPU path"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    dec, asr, lm = build_models(dev)
+    dec.fast_math = bool(args.fast_math)
+    dec.skip_dead_rows = not args.write_dead_rows
+    dec.profile_prefix = True
+    lengths = workload_lengths(world)
+    n_total = len(lengths)
+    shards = shard.plan_shards(lengths, world, MAX_RATIO)
+    batches = shard.make_batches(shards[rank], lengths, args.max_utts, args.max_padded_frames)
+    cap = int(np.ceil(lengths.max() * MAX_RATIO)) + 1
+    rows = max(len(s) for s in shards)
+
+    host = [make_features(b, lengths, pin=True) for b in batches]            # pinned host buffers
+    resident = [(f.to(dev), l.to(dev)) for f, l in host]                      # HBM-resident copies
+    h2d_bytes = sum(f.numel() * 4 + l.numel() * 8 for f, l in host)
+    in_bytes = sum(f.numel() * 4 for f, _ in resident)
+
+    def one_pass(from_host):
+        parts, ids = [], []
+        for b, hb, rb in zip(batches, host, resident):
+            if from_host:
+                feat, fl = hb[0].to(dev, non_blocking=True), hb[1].to(dev, non_blocking=True)
+            else:
+                feat, fl = rb
+            parts.append(dec.decode_batch(feat, fl, return_arrays=True))      # N-best read back to the host
+            ids.extend(b)
+        width = max(p[0].shape[2] for p in parts)
+        pad = lambda a: torch.nn.functional.pad(a, (0, width - a.shape[2]))
+        tok = torch.cat([pad(p[0]) for p in parts]); sc = torch.cat([pad(p[1]) for p in parts])
+        ln = torch.cat([p[2] for p in parts]); avg = torch.cat([p[3] for p in parts]); n = torch.cat([p[4] for p in parts])
+        local_buf = shard.pack_nbest(ids, tok, sc, ln, avg, n, cap, rows)
+        full = shard.gather_nbest(local_buf, dev)                             # the one collective (no-op at N=1)
+        return local_buf, full
+
+    def timed(from_host, steps, warmup):
+        for _ in range(warmup):
+            one_pass(from_host)
+        dec.prefix_events = []
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = ops.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            local_buf, full = one_pass(from_host)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        clocks = sampler.stop() if rank == 0 else None
+        return float(ms.item()), ops.launch_count() - l0, clocks, local_buf, full
+
+    ms, launches, clocks, local_buf, full = timed(False, args.steps, args.warmup)
+    # prefix-score kernel: per-launch CUDA-event durations collected inside the timed region
+    ev = dec.prefix_events
+    k_ms = [a.elapsed_time(b) for a, b, _, _ in ev]
+    units_formula = float(sum(u for _, _, u, _ in ev))
+    units_rows = float(sum(r for _, _, _, r in ev))
+    k_total_ms = float(sum(k_ms))
+    bytes_per_unit = 12.0 + 12.0 / dec.ctc_beam_size
+    peak, peak_src = load_peaks()
+    achieved = units_formula * bytes_per_unit / (k_total_ms * 1e-3) / 1e9 if k_total_ms > 0 else 0.0
+    achieved_rows = units_rows * bytes_per_unit / (k_total_ms * 1e-3) / 1e9 if k_total_ms > 0 else 0.0
+    dec.profile_prefix = False
+
+    e2e_ms, _, _, _, _ = timed(True, args.steps, 1)
+    stats_units = units_formula / max(1, args.steps)
+
+    if rank != 0:
+        return
+    ok = int((full[:, 0] >= 0).sum()) == n_total
+    line = {
+        "metric": METRIC, "value": n_total * args.steps / (ms * 1e-3), "unit": "utts/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: char V=31 VGG+BLSTM CTC-attention (librispeech_asr.yaml dims, vgg=1) + 4x1024 RNNLM, "
+                               "beam 8, ctc 0.5, lm 0.5, max_len_ratio 0.2, %d utts/GPU dev-clean-like lengths, random init" % N_UTTS,
+                   "utterances": n_total, "batches_per_gpu": len(batches), "max_utts_per_batch": args.max_utts,
+                   "prefix_fast_math": bool(args.fast_math), "skip_dead_rows": not args.write_dead_rows,
+                   "l2": "inputs (%.1f GB features + GB-scale prefix states per batch) exceed the 126 MB L2; no flush needed" % (in_bytes / 1e9),
+                   "parallelism": "utterance shards x%d, one all-gather of N-best" % world},
+        "e2e": {"value": n_total * args.steps / (e2e_ms * 1e-3), "unit": "utts/s",
+                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(local_buf.numel() * 4)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "prefix_score_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_cand_frame": bytes_per_unit, "cand_frames_per_step": stats_units,
+                     "kernel_ms_per_step": k_total_ms / max(1, args.steps), "launches_per_step": len(ev) / max(1, args.steps),
+                     "kernel_share_of_step": k_total_ms / ms,
+                     "achieved_computed_rows_only": achieved_rows, "frac_computed_rows_only": achieved_rows / peak,
+                     "cand_frames_per_s": units_formula / (k_total_ms * 1e-3) if k_total_ms > 0 else 0.0},
+        "nbest_complete": bool(ok),
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(args, sample_utts=args.cpu_sample)
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference, one utterance per worker process (the reference fans
+# utterances out to joblib processes, bin/test_asr.py:138-139)
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(job):
+    uid, n = job
+    import torch as th
+    th.set_num_threads(1)
+    from oracle import beam_oracle as BO
+    from e2e_asr_pytorch_b200 import synth
+    global _CPU_MODELS
+    try:
+        asr, lm = _CPU_MODELS
+    except NameError:
+        asr, lm = synth.build_asr(VOCAB, seed=0), synth.build_lm(VOCAB, seed=1)
+        _CPU_MODELS = (asr, lm)
+    feat = synth.utterance(uid, n)[None]
+    trace = []
+    t0 = time.time()
+    with th.no_grad():
+        nb = BO.decode_utterance(asr, feat, th.LongTensor([n]), BEAM, MIN_RATIO, MAX_RATIO, lm=lm,
+                                 lm_weight=LM_W, ctc_weight=CTC_W, trace=None)
+    steps = int(np.ceil(n * MAX_RATIO))
+    frames = n // 4
+    return time.time() - t0, (1 + (steps - 1) * BEAM) * int(1.5 * BEAM) * frames, len(nb)
+
+
+def cpu_sample_jobs(n_jobs, frames=240):
+    """Bounded sample: ``n_jobs`` utterances of ``frames`` input frames each (short on purpose — a
+    median 6.4 s utterance costs ~1 CPU-minute; utts/s therefore FLATTERS the CPU)."""
+    return [(100000 + k, frames) for k in range(n_jobs)]
+
+
+def cpu_pass(pool, jobs):
+    t0 = time.time()
+    res = pool.map(_cpu_worker, jobs)
+    wall = time.time() - t0
+    return wall, sum(r[1] for r in res)
+
+
+def cpu_baseline(args, sample_utts=None):
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    procs = max(1, min(cores, args.cpu_procs or cores))
+    n_jobs = sample_utts or procs
+    jobs = cpu_sample_jobs(n_jobs, args.cpu_frames)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        wall, units = cpu_pass(pool, jobs)
+    return {"value": n_jobs / wall, "unit": "utts/s", "cores": procs, "kind": "port",
+            "sample": "%d synthetic utts of %d input frames (%.1f s audio) each, one per process, oracle/beam_oracle.py "
+                      "(numpy prefix score + PyTorch-CPU modules), %.1f s wall" % (n_jobs, args.cpu_frames, args.cpu_frames / 100.0, wall),
+            "cand_frames_per_s": units / wall}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    procs = max(1, min(cores, args.cpu_procs or cores))
+    jobs = cpu_sample_jobs(args.cpu_sample or procs, args.cpu_frames)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        for _ in range(args.warmup):
+            cpu_pass(pool, jobs[:procs])
+        t0 = time.time()
+        units = 0
+        for _ in range(args.steps):
+            w, u = cpu_pass(pool, jobs)
+            units += u
+        wall = time.time() - t0
+    value = len(jobs) * args.steps / wall
+    sample = "%d synthetic utts of %d input frames per step, one per process, oracle port of the reference " \
+             "(reference is Python under /root/reference and cannot travel)" % (len(jobs), args.cpu_frames)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "utts/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2 model/decoder settings on a bounded sample: " + sample},
+        "cpu_baseline": {"value": value, "unit": "utts/s", "cores": procs, "kind": "port", "sample": sample,
+                         "cand_frames_per_s": units / wall},
+        "e2e": {"value": value, "unit": "utts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--max-utts", type=int, default=1024)
+    ap.add_argument("--max-padded-frames", type=int, default=700000)
+    ap.add_argument("--fast-math", type=int, default=0)
+    ap.add_argument("--write-dead-rows", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-procs", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--cpu-frames", type=int, default=240)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -168,9 +168,12 @@ prefix_score_kernel(const PrefixParams p)
                 const int tt_first = start - t0;              // first frame of this tile that is computed
                 if (tt_first > 0) {
                     const int stop = min(tt_first, rows);
+                    // Row 0 of an empty-prefix extension, (x[0,c], logzero), is read back by the child's
+                    // first frame (its start is also 1), so it is written even when dead rows are skipped.
+                    if (t0 == 0 && plen == 0) rout[0] = make_float2(nb, E2E_CTC_LOGZERO);
                     if (fill_dead)
                         for (; tt < stop; ++tt)
-                            rout[(long long)(t0 + tt) * LU] = (t0 + tt == 0 && plen == 0) ? make_float2(nb, E2E_CTC_LOGZERO) : dead;
+                            if (!(t0 + tt == 0 && plen == 0)) rout[(long long)(t0 + tt) * LU] = dead;
                     tt = stop;
                 }
 #pragma unroll 4

@@ -115,6 +115,8 @@ class BeamDecoder(nn.Module):
         # knobs of the device path (not part of the reference interface)
         self.fast_math = False          # MUFU log-add-exp in the prefix-score kernel
         self.skip_dead_rows = True      # do not write state rows t < len(prefix) nobody reads back
+        self.profile_prefix = False     # bench.py: CUDA-event pair around every prefix-score launch
+        self.prefix_events = []         # (start, end, cand_frames [SURVEY §8d formula], cand_frames actually computed)
         self.last_stats = {}
 
     def create_msg(self):
@@ -167,15 +169,26 @@ class BeamDecoder(nn.Module):
                 r_a = torch.empty((n_utts, t_max, beam * n_cand, 2), dtype=torch.float32, device=dev)
                 r_b = torch.empty_like(r_a)
             pflags = (L.PREFIX_FAST_MATH if self.fast_math else 0) | (L.PREFIX_SKIP_DEAD_ROWS if self.skip_dead_rows else 0)
+            if self.profile_prefix and self.apply_ctc:
+                t_np, s_np = enc_len.cpu().numpy().astype(np.int64), max_len.numpy().astype(np.int64)
 
             for step in range(n_steps):                                            # decode.py:104
                 att_logits, lm_logits = stepper.step(buf.last_tok.view(-1).long())
                 ops.beam_candidates(att_logits, n_utts, beam, vocab, n_cand, buf.n_active, buf.att_stats, buf.cand)
                 if self.apply_ctc:
                     r_cur = r_a if (step % 2 == 0) else r_b
+                    if self.profile_prefix:
+                        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        ev0.record()
                     ops.ctc_prefix_score(x, vocab, enc_len32, r_prev, buf.prev_lane.view(-1), buf.last_tok.view(-1),
                                          buf.prefix_len.view(-1), buf.n_active, buf.cand, beam, n_cand, pflags,
                                          psi=buf.psi, r_out=r_cur, status=buf.status)
+                    if self.profile_prefix:
+                        ev1.record()
+                        act = s_np > step                     # utterances that still decode at this step
+                        hyps = (1 if step == 0 else beam) * n_cand      # H_s * C (n_live < B after an <eos> closure is ignored)
+                        self.prefix_events.append((ev0, ev1, float(hyps * t_np[act].sum()),
+                                                   float(hyps * np.maximum(t_np[act] - max(1, step), 0).sum())))
                     r_prev = r_cur
                 ops.beam_combine_prune(buf, att_logits, lm_logits, vocab, step, ctc_w, lm_w, EOS_THRESHOLD)
                 stepper.reorder(buf.parent_slot)

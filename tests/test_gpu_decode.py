@@ -21,6 +21,17 @@ SCORE_TOL = 2e-4    # |mean score| agreement for identical sequences
 TIE_TOL = 5e-4      # score gap below which two hypotheses count as tied
 
 
+_CPU = {}
+
+
+def _cpu_copy(m):
+    """The decoder's .to(cuda) moves the shared modules; the oracle needs CPU twins."""
+    import copy
+    if id(m) not in _CPU:
+        _CPU[id(m)] = (m, copy.deepcopy(m).cpu())
+    return _CPU[id(m)][1]
+
+
 def _models(vocab=31, peak=4.0):
     from e2e_asr_pytorch_b200 import synth
     asr = synth.build_asr(vocab, synth.TINY_ASR_CFG, seed=0, peak=peak)
@@ -33,6 +44,7 @@ def _models(vocab=31, peak=4.0):
 
 def _oracle_nbest(asr, lm, feat, n, beam, lm_w, ctc_w, max_ratio=0.2):
     from oracle import beam_oracle as BO
+    asr, lm = _cpu_copy(asr), _cpu_copy(lm)
     with torch.no_grad():
         nb = BO.decode_utterance(asr, feat[None, :n], torch.LongTensor([n]), beam, 0.01, max_ratio,
                                  lm=lm if lm_w > 0 else None, lm_weight=lm_w, ctc_weight=ctc_w)

@@ -54,6 +54,7 @@ def test_ctc_log_softmax_without_relu(cuda):
 # ----------------------------------------------------------------------------------------------
 def _chain(cuda, rng, n_utts, t_lens, vocab, beam, n_cand, n_steps, flags=0, check_states=True):
     ops, L = _ops()
+    ulps = 4.0 if (flags & L.PREFIX_FAST_MATH) else 2.0
     from oracle import c_oracle as CO
     t_max = max(t_lens)
     post = posteriors(rng, n_utts, t_max, vocab)                               # [U,T,V]
@@ -100,15 +101,15 @@ def _chain(cuda, rng, n_utts, t_lens, vocab, beam, n_cand, n_steps, flags=0, che
             outs = []
             for b, (g, st) in enumerate(beams[u]):
                 p_o, r_o = CO.extend(post[u, :n], len(g), g[-1] if g else 0, st, cand[u, b].tolist())
-                worst = max(worst, assert_prefix_close(psi[u, b], p_o, "psi step %d utt %d slot %d" % (step, u, b)))
+                worst = max(worst, assert_prefix_close(psi[u, b], p_o, "psi step %d utt %d slot %d" % (step, u, b), ulps))
                 if check_states:
                     got = r_host[u, :n, b].transpose(1, 0, 2)                  # [C,T,2]
                     if flags & L.PREFIX_SKIP_DEAD_ROWS:
-                        first = max(1, len(g))
+                        first = max(1, len(g)) if g else 0      # row 0 of an empty-prefix extension is always written
                         got, r_cmp = got[:, first:], r_o[:, first:]
                     else:
                         r_cmp = r_o
-                    worst = max(worst, assert_prefix_close(got, r_cmp, "r step %d utt %d slot %d" % (step, u, b)))
+                    worst = max(worst, assert_prefix_close(got, r_cmp, "r step %d utt %d slot %d" % (step, u, b), ulps))
                 outs.append((g, r_o))
             # survivors: random (parent, candidate) pairs, at most `beam`
             picks = [(b, j) for b in range(len(outs)) for j in range(n_cand)]
