@@ -19,6 +19,7 @@ STATUS_FINISHED_OVERFLOW = 4
 PREFIX_FULL = 1
 PREFIX_SKIP_DEAD_ROWS = 2
 PREFIX_FAST_MATH = 4
+PREFIX_LIBM_MATH = 8
 BEAM_USE_CTC = 1
 BEAM_USE_LM = 2
 

@@ -36,7 +36,7 @@ struct PrefixParams {
     int hyps_per_cta;     // rows of the phi tile
 };
 
-template <bool kGather, bool kFast>
+template <bool kGather, int kMath>
 __global__ void __launch_bounds__(kMaxThreads)
 prefix_score_kernel(const PrefixParams p)
 {
@@ -62,6 +62,8 @@ prefix_score_kernel(const PrefixParams p)
     int *s_plane = reinterpret_cast<int *>(phis + (size_t)H * kTile);
     int *s_red = s_plane + H;
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_red + 2 + ((H & 1) ? 1 : 0));   // 8-byte aligned
+    float4 *lut_base = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(bars + 2) + 15) & ~(uintptr_t)15);
+    const float4 *lut = lut_base + (tid & (kLutCopies - 1));                           // this lane's replica
     float *xb_g = xs + (size_t)kTile * nt;       // gather variant only
 
     // ---- per-lane setup ---------------------------------------------------------------------
@@ -84,6 +86,7 @@ prefix_score_kernel(const PrefixParams p)
     const bool special = full ? (tok == (plen > 0 ? ltok : 0)) : (plen > 0 && tok == ltok);
 
     if (tid == 0) { s_red[0] = 0x7fffffff; }
+    if (kMath == kMathLut) softplus_lut_to_smem(lut_base, tid, nt);
     for (int i = tid; i < H; i += nt) {
         const int hh = h_lo + i;
         s_plane[i] = (hh < live) ? p.prev_lane[u * p.B + hh] : -1;
@@ -141,8 +144,8 @@ prefix_score_kernel(const PrefixParams p)
                 if (pl >= 0 && ts >= 0 && ts < T && tt < rows) {
                     const float2 a = __ldg(rprev_u + (long long)ts * p.lanes_prev + pl);
                     float2 ph;
-                    ph.x = logaddexp<kFast>(a.x, a.y);
-                    ph.y = full ? logaddexp<kFast>(E2E_CTC_LOGZERO, a.y) : a.y;
+                    ph.x = logaddexp<kMath>(a.x, a.y, lut);
+                    ph.y = full ? logaddexp<kMath>(E2E_CTC_LOGZERO, a.y, lut) : a.y;
                     phis[i] = ph;
                 }
             }
@@ -176,17 +179,24 @@ prefix_score_kernel(const PrefixParams p)
                             if (!(t0 + tt == 0 && plen == 0)) rout[(long long)(t0 + tt) * LU] = dead;
                     tt = stop;
                 }
+                // pointer-bumped inner loop: 3 LDS (phi pair, x_c, x_blank), 3 log-add-exp, 1 STG.64
+                const float2 *php = ph_row + tt;
+                const float *xcp = xt + tt * pitch + col;
+                const float *xbp = kGather ? (xb_g + tt) : (xt + tt * pitch + E2E_CTC_BLANK);
+                const int xb_step = kGather ? 1 : pitch;
+                float2 *outp = rout + (long long)(t0 + tt) * LU;
 #pragma unroll 4
                 for (; tt < rows; ++tt) {
-                    const float2 ph = ph_row[tt];
+                    const float2 ph = *php;
                     const float phi = special ? ph.y : ph.x;
-                    const float xc = xt[tt * pitch + col];
-                    const float xb = kGather ? xb_g[tt] : xt[tt * pitch + E2E_CTC_BLANK];
-                    const float nnb = __fadd_rn(logaddexp<kFast>(nb, phi), xc);
-                    const float nbl = __fadd_rn(logaddexp<kFast>(bl, nb), xb);
-                    psi = logaddexp<kFast>(psi, __fadd_rn(phi, xc));
+                    const float xc = *xcp;
+                    const float xb = *xbp;
+                    const float nnb = __fadd_rn(logaddexp<kMath>(nb, phi, lut), xc);
+                    const float nbl = __fadd_rn(logaddexp<kMath>(bl, nb, lut), xb);
+                    psi = logaddexp<kMath>(psi, __fadd_rn(phi, xc), lut);
                     nb = nnb; bl = nbl;
-                    rout[(long long)(t0 + tt) * LU] = make_float2(nnb, nbl);
+                    *outp = make_float2(nnb, nbl);
+                    ++php; xcp += pitch; xbp += xb_step; outp += LU;
                 }
             }
             __syncthreads();
@@ -197,7 +207,7 @@ prefix_score_kernel(const PrefixParams p)
     if (run) {
         if (!full && tok == E2E_CTC_EOS) {       // P(<eos> | g) = P(g)   (src/ctc.py:106-107)
             const float2 a = __ldg(rprev_u + (long long)(T - 1) * p.lanes_prev + s_plane[h - h_lo]);
-            psi = logaddexp<kFast>(a.x, a.y);
+            psi = logaddexp<kMath>(a.x, a.y, lut);
             // psi aliases r[start-1,0,:] in the reference when the time loop never runs (src/ctc.py:85)
             if (start >= T && fill_dead) rout[(long long)(start - 1) * LU] = make_float2(psi, E2E_CTC_LOGZERO);
         }
@@ -211,7 +221,10 @@ static size_t prefix_smem_bytes(bool gather, int nt, int Vp, int H)
 {
     size_t xs_floats = gather ? (size_t)kTile * nt + kTile : (size_t)2 * kTile * Vp;
     xs_floats = (xs_floats + 3) & ~(size_t)3;
+    // xs | phis | s_plane[H] | s_red[2] (+pad) | bars[2] | LUT replicas.  xs and phis are multiples of 16 bytes and
+    // 4H + 8 (+4 if H is odd) + 16 is a multiple of 8, so one more 8-byte pad makes the LUT 16-byte aligned when needed.
     size_t b = xs_floats * 4 + (size_t)H * kTile * 8 + (size_t)H * 4 + 8 + ((H & 1) ? 4 : 0) + 16;
+    b += (size_t)kLutNodes * kLutCopies * 16 + 16;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -254,10 +267,15 @@ extern "C" int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int
     if (grid > 0x7fffffffLL) return set_error(E2E_ERR_UNSUPPORTED, "e2e_ctc_prefix_score: grid too large");
 
     const bool gather = Vp > kMaxRowFloats;
-    const bool fast = (flags & E2E_PREFIX_FAST_MATH) != 0;
+    const int math = (flags & E2E_PREFIX_FAST_MATH) ? kMathMufu : ((flags & E2E_PREFIX_LIBM_MATH) ? kMathLibm : kMathLut);
     const size_t smem = prefix_smem_bytes(gather, nt, Vp, p.hyps_per_cta);
-    void (*kern)(PrefixParams) = gather ? (fast ? prefix_score_kernel<true, true> : prefix_score_kernel<true, false>)
-                                        : (fast ? prefix_score_kernel<false, true> : prefix_score_kernel<false, false>);
+    void (*kern)(PrefixParams);
+    if (gather)
+        kern = math == kMathLut ? prefix_score_kernel<true, kMathLut>
+                                : (math == kMathMufu ? prefix_score_kernel<true, kMathMufu> : prefix_score_kernel<true, kMathLibm>);
+    else
+        kern = math == kMathLut ? prefix_score_kernel<false, kMathLut>
+                                : (math == kMathMufu ? prefix_score_kernel<false, kMathMufu> : prefix_score_kernel<false, kMathLibm>);
     if (smem > 48 * 1024) {
         if (smem > 200 * 1024) return set_error(E2E_ERR_UNSUPPORTED, "e2e_ctc_prefix_score: %zu bytes of shared memory needed", smem);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -55,7 +55,9 @@ extern "C" {
 #define E2E_PREFIX_FULL           1 /* full_compute semantics (src/ctc.py:29-66): candidates are 0..V-1 */
 #define E2E_PREFIX_SKIP_DEAD_ROWS 2 /* do not write state rows t < start (they are never read back by
                                        the batched beam search; the drop-in scorer always writes them) */
-#define E2E_PREFIX_FAST_MATH      4 /* MUFU ex2/lg2 based log-add-exp instead of expf/log1pf            */
+#define E2E_PREFIX_FAST_MATH      4 /* MUFU ex2/lg2 log-add-exp (abs. error ~3e-7) instead of the default
+                                       table-based one (within one fp32 rounding of exact)              */
+#define E2E_PREFIX_LIBM_MATH      8 /* CUDA expf/log1pf log-add-exp: slow cross-check of the default     */
 
 /* flags of e2e_beam_combine_prune */
 #define E2E_BEAM_USE_CTC 1

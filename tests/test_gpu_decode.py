@@ -106,23 +106,27 @@ def test_decode_without_ctc_and_without_lm(cuda):
             _compare(out[k], ora, "no-ctc lm %.1f utt %d" % (lm_w, k))
 
 
-def test_decode_eos_termination(cuda):
-    """Bias the speller towards <eos> so the threshold branch (decode.py:232-241) and the
-    closed-hypothesis bookkeeping run; random-init weights alone never close a hypothesis."""
+@pytest.mark.parametrize("eos_bias,blank_bias,ctc_w,lm_w", [(3.0, 6.0, 0.5, 0.3), (1.0, 6.0, 0.5, 0.0), (4.0, 0.0, 0.0, 0.3), (4.0, 0.0, 0.0, 0.0)])
+def test_decode_eos_termination(cuda, eos_bias, blank_bias, ctc_w, lm_w):
+    """Random-init weights alone never close a hypothesis: bias the speller
+    towards <eos> and the CTC head towards blank so that the threshold branch
+    (decode.py:232-241), the closed-hypothesis list and the final re-ranking run; with CTC off
+    and the LM on, the reference's aliased eos test is exercised too."""
     from e2e_asr_pytorch_b200 import BeamDecoder, synth
     asr, lm, lm_path, lm_cfg = _models()
     with torch.no_grad():
-        asr.decoder.char_trans.bias[1] += 6.0
+        asr.decoder.char_trans.bias[1] += eos_bias
+        asr.ctc_layer[0].bias[0] += blank_bias
     lens = [64, 120, 92]
     feat, fl = synth.padded_batch([0, 1, 2], lens)
-    dec = BeamDecoder(asr, None, 4, 0.01, 0.2, lm_path=lm_path, lm_config=lm_cfg, lm_weight=0.3, ctc_weight=0.5).to(cuda)
+    dec = BeamDecoder(asr, None, 4, 0.01, 0.2, lm_path=lm_path, lm_config=lm_cfg, lm_weight=lm_w, ctc_weight=ctc_w).to(cuda)
     out = dec.decode_batch(feat.to(cuda), fl.to(cuda))
     closed = 0
     for k, n in enumerate(lens):
-        ora = _oracle_nbest(asr, lm, feat[k], n, 4, 0.3, 0.5)
-        assert [len(h.outIndex) for h in out[k]] == [len(o[0]) for o in ora]
+        ora = _oracle_nbest(asr, lm, feat[k], n, 4, lm_w, ctc_w)
+        assert [len(h.outIndex) for h in out[k]] == [len(o[0]) for o in ora], (k, [h.outIndex for h in out[k]], [o[0].tolist() for o in ora])
         _compare(out[k], ora, "eos utt %d" % k)
-        closed += sum(1 for o in ora if len(o[0]) < int(np.ceil(n * 0.2)))
+        closed += sum(1 for o in ora if o[0][-1] == 1 and len(o[0]) < int(np.ceil(n * 0.2)))
     assert closed > 0, "the fixture did not exercise <eos> termination"
 
 
