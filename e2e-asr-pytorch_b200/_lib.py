@@ -15,7 +15,6 @@ CTC_LOGZERO = -100000000.0
 DEC_LOG_ZERO = -10000000.0
 STATUS_PREFIX_TOO_LONG = 1
 STATUS_TOKEN_NOT_CAND = 2
-STATUS_FINISHED_OVERFLOW = 4
 PREFIX_FULL = 1
 PREFIX_SKIP_DEAD_ROWS = 2
 PREFIX_FAST_MATH = 4

@@ -215,18 +215,32 @@ beam_combine_prune_kernel(const CombineParams p)
     __syncthreads();
 
     // ---- closed hypotheses (decode.py:167-170): parent order, only once step >= min_len ---------
+    // The list is kept stably sorted by mean score and truncated to fin_cap entries: the final
+    // selection (decode.py:180-183) is a stable sort of closed ++ live hypotheses cut to B, so with
+    // fin_cap >= B nothing that could be returned is ever dropped.
     if (threadIdx.x == 0 && p.step >= p.min_len[u]) {
         int fc = p.fin_count[u];
+        const long long base = (long long)u * p.fin_cap;
         for (int b = 0; b < live; ++b) {
             if (!term[b]) continue;
-            if (fc >= p.fin_cap) { if (p.status) atomicOr(p.status + u, E2E_STATUS_FINISHED_OVERFLOW); break; }
-            const long long o = (long long)u * p.fin_cap + fc;
             const float ps = p.score_sum[u * B + b];
-            p.fin_step[o] = p.step;
-            p.fin_parent[o] = b;
-            p.fin_score[o] = term_sc[b];
-            p.fin_sum[o] = (p.step == 0) ? term_sc[b] : __fadd_rn(ps, term_sc[b]);
-            ++fc;
+            const float fsum = (p.step == 0) ? term_sc[b] : __fadd_rn(ps, term_sc[b]);
+            const float key = __fdiv_rn(fsum, (float)(p.step + 1));
+            int pos = fc;                                   // stable: after every entry with key >= ours
+            while (pos > 0 && !(__fdiv_rn(p.fin_sum[base + pos - 1], (float)(p.fin_step[base + pos - 1] + 1)) >= key)) --pos;
+            if (pos >= p.fin_cap) continue;
+            const int last = fc < p.fin_cap ? fc : p.fin_cap - 1;
+            for (int i = last; i > pos; --i) {
+                p.fin_step[base + i] = p.fin_step[base + i - 1];
+                p.fin_parent[base + i] = p.fin_parent[base + i - 1];
+                p.fin_score[base + i] = p.fin_score[base + i - 1];
+                p.fin_sum[base + i] = p.fin_sum[base + i - 1];
+            }
+            p.fin_step[base + pos] = p.step;
+            p.fin_parent[base + pos] = b;
+            p.fin_score[base + pos] = term_sc[b];
+            p.fin_sum[base + pos] = fsum;
+            if (fc < p.fin_cap) ++fc;
         }
         p.fin_count[u] = fc;
     }
@@ -380,6 +394,7 @@ extern "C" int e2e_beam_combine_prune(const float *att_logits, int ld_att, const
         return set_error(E2E_ERR_ARG, "e2e_beam_combine_prune: flags need lm_logits / cand+psi");
     if (U <= 0 || B <= 0 || B > 32 || V <= 0 || step < 0 || fin_cap <= 0 || ld_att < V || (use_lm && ld_lm < V))
         return set_error(E2E_ERR_ARG, "e2e_beam_combine_prune: bad size (beam size must be 1..32)");
+    if (fin_cap < B) return set_error(E2E_ERR_ARG, "e2e_beam_combine_prune: fin_cap must be >= B");
     CombineParams p;
     p.att_logits = att_logits; p.ld_att = ld_att; p.att_stats = reinterpret_cast<const float2 *>(att_stats);
     p.lm_logits = lm_logits; p.ld_lm = ld_lm; p.cand = cand; p.psi = psi;

@@ -2,28 +2,36 @@
 // Replaces CTCPrefixScore.cheap_compute / full_compute (src/ctc.py:29-108) for every live
 // (utterance, beam slot, candidate) in one launch.
 //
-// Mapping.  One thread owns one prefix-state lane l = slot*C + j of one utterance and walks the
-// encoder frames t = start..T-1 sequentially in fp32 (the reference's order), carrying
-// (r_nonblank, r_blank, psi) in registers.  A CTA covers `blockDim.x` consecutive lanes of ONE
-// utterance, so all of its threads share the utterance's posterior rows x[t][u][:] and the few
-// parent states r_prev[t][parent].  Frames are processed in tiles of kTile:
+// Mapping.  A prefix-state "lane" l = slot*C + j of one utterance walks the encoder frames
+// t = start..T-1 sequentially in fp32 (the reference's order).  Per frame it needs
+//     r0' = logaddexp(r0, phi) + x_c      r1' = logaddexp(r1, r0) + x_blank       (the recurrence)
+//     psi = logaddexp(psi, phi + x_c)                                              (a running reduction)
+// psi never feeds back into r, so every lane is served by TWO threads of the same CTA: a
+// "state" thread carries (r0, r1) and streams them out as one coalesced float2 per frame, a
+// "psi" thread carries psi.  That doubles the independent dependency chains in flight per
+// utterance, which is what the sequential-in-T recursion is starved of.
+// A CTA covers up to 128 consecutive lanes of ONE utterance (2x that many threads), so its
+// threads share the utterance's posterior rows x[t][u][:] and the few parent states.
+// Frames are processed in tiles of kTile:
 //   * "rows" variant (Vp <= kMaxRowFloats): the tile's posterior rows are brought into shared
 //     memory by the TMA engine (cp.async.bulk, one 16B-aligned row per copy, completion on an
 //     mbarrier), double buffered, so the gather x[t][cand] becomes a conflict-free LDS;
-//   * "gather" variant (large vocabularies): each lane fetches its own column x[t][u][cand]
-//     for the whole tile with independent loads and parks them in shared memory.
-//   Per tile the CTA first turns the parents' states into phi tiles in shared memory
+//   * "gather" variant (large vocabularies): each state thread fetches its own column
+//     x[t][u][cand] for the whole tile with independent loads and parks it in shared memory.
+//   The parents' states are turned into phi tiles in shared memory once per hypothesis
 //     phi[h][t] = ( logaddexp(r_prev[t][0], r_prev[t][1]),  r_prev[t][1] )
-//   (once per hypothesis instead of once per candidate), then every lane runs
-//     r0' = logaddexp(r0, phi) + x_c ; r1' = logaddexp(r1, r0) + x_blank ; psi = logaddexp(psi, phi + x_c)
-//   and streams (r0', r1') out as one coalesced float2 per lane per frame.
+//   and are software pipelined: the global loads for tile k+1 are issued before tile k is
+//   computed, so one __syncthreads per tile is all the synchronisation there is.
 #include "common.cuh"
 
 namespace e2e {
 
 constexpr int kTile = 32;            // frames per shared-memory tile
+constexpr int kPhiPitch = kTile + 1; // float2 pitch of a phi row (odd: no bank conflicts across hypotheses)
 constexpr int kMaxRowFloats = 256;   // rows variant up to 1 KB per posterior row
-constexpr int kMaxThreads = 256;
+constexpr int kMaxLanes = 128;       // lanes per CTA (threads = 2 x lanes)
+constexpr int kPrefetch = 2;         // phi entries per thread held in registers across a tile
+constexpr int kLutBytes = kLutNodes * kLutCopies * 16;
 
 struct PrefixParams {
     const float *x; int Tmax, U, Vp, V;
@@ -33,41 +41,53 @@ struct PrefixParams {
     int B, C, flags;
     float *psi; float2 *r_out; int *status;
     int chunks_per_utt;   // CTAs per utterance
+    int lanes_per_cta;    // multiple of 32; blockDim.x = 2 * lanes_per_cta
     int hyps_per_cta;     // rows of the phi tile
 };
 
+__host__ __device__ inline size_t prefix_xs_bytes(bool gather, int lanes, int Vp)
+{
+    size_t f = gather ? (size_t)kTile * lanes + kTile : (size_t)2 * kTile * Vp;
+    return ((f + 3) & ~(size_t)3) * 4;
+}
+__host__ __device__ inline size_t prefix_phis_bytes(int H) { return (size_t)2 * H * kPhiPitch * 8; }
+
 template <bool kGather, int kMath>
-__global__ void __launch_bounds__(kMaxThreads)
+__global__ void __launch_bounds__(2 * kMaxLanes, 5)
 prefix_score_kernel(const PrefixParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int nl = p.lanes_per_cta;
+    const bool psi_role = tid >= nl;              // warp uniform (nl is a multiple of 32)
+    const int lt = psi_role ? tid - nl : tid;     // lane index within the CTA
     const int u = blockIdx.x / p.chunks_per_utt;
     const int chunk = blockIdx.x % p.chunks_per_utt;
     const int T = p.enc_len ? p.enc_len[u] : p.Tmax;
     const int live = p.n_live ? p.n_live[u] : p.B;
     const int C = p.C, LU = p.B * p.C;
-    const int lane0 = chunk * nt;                 // first lane (within the utterance) of this CTA
+    const int lane0 = chunk * nl;                 // first lane (within the utterance) of this CTA
     if (T <= 0 || lane0 >= live * C) return;      // nothing to do for this CTA (uniform exit)
     const bool full = (p.flags & E2E_PREFIX_FULL) != 0;
     const bool fill_dead = (p.flags & E2E_PREFIX_SKIP_DEAD_ROWS) == 0;
 
-    // ---- shared memory carve-up -------------------------------------------------------------
-    // rows:   xs[2][kTile][Vp] | phis[H][kTile] float2 | s_plane[H] | s_red[2] | bars[2]
-    // gather: xs[kTile][nt]    | xb[kTile] | phis | s_plane | s_red
+    // ---- shared memory: LUT replicas | x tiles | phi tiles (x2) | s_plane[H] | s_red[2] | mbarriers[2]
     const int H = p.hyps_per_cta;
-    float *xs = reinterpret_cast<float *>(smem_raw);
-    const size_t xs_floats = kGather ? (size_t)kTile * nt + kTile : (size_t)2 * kTile * p.Vp;
-    float2 *phis = reinterpret_cast<float2 *>(xs + ((xs_floats + 3) & ~(size_t)3));
-    int *s_plane = reinterpret_cast<int *>(phis + (size_t)H * kTile);
+    const size_t xs_off = kLutBytes;
+    const size_t phis_off = xs_off + prefix_xs_bytes(kGather, nl, p.Vp);
+    const size_t misc_off = phis_off + prefix_phis_bytes(H);
+    const size_t bars_off = (misc_off + (size_t)(H + 2) * 4 + 7) & ~(size_t)7;
+    float4 *lut_base = reinterpret_cast<float4 *>(smem_raw);
+    float *xs = reinterpret_cast<float *>(smem_raw + xs_off);
+    float2 *phis = reinterpret_cast<float2 *>(smem_raw + phis_off);
+    int *s_plane = reinterpret_cast<int *>(smem_raw + misc_off);
     int *s_red = s_plane + H;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_red + 2 + ((H & 1) ? 1 : 0));   // 8-byte aligned
-    float4 *lut_base = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(bars + 2) + 15) & ~(uintptr_t)15);
-    const float4 *lut = lut_base + (tid & (kLutCopies - 1));                           // this lane's replica
-    float *xb_g = xs + (size_t)kTile * nt;       // gather variant only
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + bars_off);
+    const float4 *lut = lut_base + (tid & (kLutCopies - 1));      // this thread's replica
+    float *xb_g = xs + (size_t)kTile * nl;                        // gather variant only
 
-    // ---- per-lane setup ---------------------------------------------------------------------
-    const int lane_u = lane0 + tid;               // lane within the utterance
+    // ---- per-lane setup (identical in both roles) ---------------------------------------------
+    const int lane_u = lane0 + lt;                // lane within the utterance
     const bool active = lane_u < live * C;
     const int h = active ? lane_u / C : 0;        // beam slot
     const int j = active ? lane_u - h * C : 0;    // candidate index
@@ -80,12 +100,12 @@ prefix_score_kernel(const PrefixParams p)
         ltok = p.last_tok[n];
     }
     const int start = plen > 1 ? plen : 1;
-    bool too_long = active && (start - 1 >= T);
-    if (too_long && p.status) atomicOr(p.status + u, E2E_STATUS_PREFIX_TOO_LONG);
+    const bool too_long = active && (start - 1 >= T);
+    if (too_long && !psi_role && p.status) atomicOr(p.status + u, E2E_STATUS_PREFIX_TOO_LONG);
     const bool run = active && !too_long;
     const bool special = full ? (tok == (plen > 0 ? ltok : 0)) : (plen > 0 && tok == ltok);
 
-    if (tid == 0) { s_red[0] = 0x7fffffff; }
+    if (tid == 0) s_red[0] = 0x7fffffff;
     if (kMath == kMathLut) softplus_lut_to_smem(lut_base, tid, nt);
     for (int i = tid; i < H; i += nt) {
         const int hh = h_lo + i;
@@ -97,7 +117,7 @@ prefix_score_kernel(const PrefixParams p)
         mbar_fence_init();
     }
     __syncthreads();
-    if (run) atomicMin(&s_red[0], start);
+    if (run && !psi_role) atomicMin(&s_red[0], start);
     __syncthreads();
     const int cta_start = s_red[0];               // 0x7fffffff if no lane runs
     const long long xrow0 = (long long)u * p.Vp;  // x[t][u][:] = x + t*U*Vp + xrow0
@@ -106,15 +126,15 @@ prefix_score_kernel(const PrefixParams p)
     const float2 *__restrict__ rprev_u = p.r_prev + ((long long)u * p.Tmax) * p.lanes_prev;
     const float2 dead = make_float2(E2E_CTC_LOGZERO, E2E_CTC_LOGZERO);
 
-    float nb = E2E_CTC_LOGZERO, bl = E2E_CTC_LOGZERO, psi = E2E_CTC_LOGZERO;
+    float nb = E2E_CTC_LOGZERO, bl = E2E_CTC_LOGZERO;
     if (run && plen == 0) nb = __ldg(p.x + xrow0 + tok);     // r[0,0,:] = x[0, c]  (src/ctc.py:82-83)
-    psi = nb;                                                  // psi = r[start-1, 0, :] (src/ctc.py:85)
+    float psi = nb;                                            // psi = r[start-1, 0, :] (src/ctc.py:85)
 
     if (cta_start != 0x7fffffff) {
         const int first_tile = cta_start / kTile;
         const int n_tiles = (T + kTile - 1) / kTile;
         // rows below the first computed tile are log-zero by construction
-        if (run && fill_dead)
+        if (run && !psi_role && fill_dead)
             for (int t = 0; t < first_tile * kTile && t < T; ++t) rout[(long long)t * LU] = dead;
 
         auto issue_rows = [&](int k) {   // warp 0: one bulk copy per posterior row of tile k
@@ -127,104 +147,138 @@ prefix_score_kernel(const PrefixParams p)
             if (tid < rows)
                 bulk_g2s(dst + (size_t)tid * p.Vp, p.x + (long long)(t0 + tid) * xstride + xrow0, (uint32_t)p.Vp * 4u, bar);
         };
-        if (!kGather && tid < 32 && first_tile < n_tiles) {
-            issue_rows(first_tile);
-            if (first_tile + 1 < n_tiles) issue_rows(first_tile + 1);
+        // phi tile k, entry (hl, tt) describes r_prev at frame k*kTile + tt - 1
+        const int n_phi = H * kTile;
+        auto phi_fetch = [&](int k, int i) -> float2 {
+            const int hl = i / kTile, tt = i - hl * kTile;
+            const int ts = k * kTile + tt - 1;
+            const int pl = s_plane[hl];
+            return (pl >= 0 && ts >= 0 && ts < T) ? __ldg(rprev_u + (long long)ts * p.lanes_prev + pl) : dead;
+        };
+        auto phi_put = [&](int k, int i, float2 a) {
+            const int hl = i / kTile, tt = i - hl * kTile;
+            float2 ph;
+            ph.x = logaddexp<kMath>(a.x, a.y, lut);
+            ph.y = full ? logaddexp<kMath>(E2E_CTC_LOGZERO, a.y, lut) : a.y;
+            phis[(size_t)(k & 1) * H * kPhiPitch + hl * kPhiPitch + tt] = ph;
+        };
+        auto phi_load = [&](int k, float2 (&reg)[kPrefetch]) {
+#pragma unroll
+            for (int q = 0; q < kPrefetch; ++q) {
+                const int i = tid + q * nt;
+                if (i < n_phi) reg[q] = phi_fetch(k, i);
+            }
+        };
+        auto phi_store = [&](int k, const float2 (&reg)[kPrefetch]) {
+#pragma unroll
+            for (int q = 0; q < kPrefetch; ++q) {
+                const int i = tid + q * nt;
+                if (i < n_phi) phi_put(k, i, reg[q]);
+            }
+            for (int i = tid + kPrefetch * nt; i < n_phi; i += nt) phi_put(k, i, phi_fetch(k, i));   // unusual shapes only
+        };
+
+        float2 pf[kPrefetch];
+#pragma unroll
+        for (int q = 0; q < kPrefetch; ++q) pf[q] = dead;
+        if (first_tile < n_tiles) {
+            if (!kGather && tid < 32) {
+                issue_rows(first_tile);
+                if (first_tile + 1 < n_tiles) issue_rows(first_tile + 1);
+            }
+            phi_load(first_tile, pf);
+            phi_store(first_tile, pf);
         }
 
         uint32_t parity[2] = {0u, 0u};
         for (int k = first_tile; k < n_tiles; ++k) {
             const int t0 = k * kTile;
             const int rows = min(kTile, T - t0);
-            // -- phi tile: entry (hl, tt) describes r_prev at frame t0+tt-1 -----------------------
-            for (int i = tid; i < H * kTile; i += nt) {
-                const int hl = i / kTile, tt = i - hl * kTile;
-                const int ts = t0 + tt - 1;
-                const int pl = s_plane[hl];
-                if (pl >= 0 && ts >= 0 && ts < T && tt < rows) {
-                    const float2 a = __ldg(rprev_u + (long long)ts * p.lanes_prev + pl);
-                    float2 ph;
-                    ph.x = logaddexp<kMath>(a.x, a.y, lut);
-                    ph.y = full ? logaddexp<kMath>(E2E_CTC_LOGZERO, a.y, lut) : a.y;
-                    phis[i] = ph;
-                }
-            }
+            if (k + 1 < n_tiles) phi_load(k + 1, pf);          // in flight while tile k is computed
             const float *xt;   // tile base: xt[tt*pitch + col]
             int pitch, col;
             if (kGather) {
-                if (active) {
+                __syncthreads();                               // everyone is done with the previous tile's columns
+                if (active && !psi_role) {
 #pragma unroll 8
                     for (int tt = 0; tt < rows; ++tt)
-                        xs[tt * nt + tid] = __ldg(p.x + (long long)(t0 + tt) * xstride + xrow0 + tok);
+                        xs[tt * nl + lt] = __ldg(p.x + (long long)(t0 + tt) * xstride + xrow0 + tok);
                 }
                 if (tid < rows) xb_g[tid] = __ldg(p.x + (long long)(t0 + tid) * xstride + xrow0 + E2E_CTC_BLANK);
-                xt = xs; pitch = nt; col = tid;
+                xt = xs; pitch = nl; col = lt;
             } else {
                 mbar_wait(&bars[k & 1], parity[k & 1]);
                 parity[k & 1] ^= 1u;
                 xt = xs + (size_t)(k & 1) * kTile * p.Vp; pitch = p.Vp; col = tok;
             }
-            __syncthreads();
+            __syncthreads();    // phi tile k and x tile k visible; all threads have left tile k-1
+            if (!kGather && tid < 32 && k > first_tile && k + 1 < n_tiles) issue_rows(k + 1);   // reuses tile k-1's buffer
             if (run) {
-                const float2 *ph_row = phis + (size_t)(h - h_lo) * kTile;
+                const float2 *ph_row = phis + (size_t)(k & 1) * H * kPhiPitch + (size_t)(h - h_lo) * kPhiPitch;
                 int tt = 0;
                 const int tt_first = start - t0;              // first frame of this tile that is computed
                 if (tt_first > 0) {
                     const int stop = min(tt_first, rows);
-                    // Row 0 of an empty-prefix extension, (x[0,c], logzero), is read back by the child's
-                    // first frame (its start is also 1), so it is written even when dead rows are skipped.
-                    if (t0 == 0 && plen == 0) rout[0] = make_float2(nb, E2E_CTC_LOGZERO);
-                    if (fill_dead)
-                        for (; tt < stop; ++tt)
-                            if (!(t0 + tt == 0 && plen == 0)) rout[(long long)(t0 + tt) * LU] = dead;
+                    if (!psi_role) {
+                        // Row 0 of an empty-prefix extension, (x[0,c], logzero), is read back by the child's
+                        // first frame (its start is also 1), so it is written even when dead rows are skipped.
+                        if (t0 == 0 && plen == 0) rout[0] = make_float2(nb, E2E_CTC_LOGZERO);
+                        if (fill_dead)
+                            for (; tt < stop; ++tt)
+                                if (!(t0 + tt == 0 && plen == 0)) rout[(long long)(t0 + tt) * LU] = dead;
+                    }
                     tt = stop;
                 }
-                // pointer-bumped inner loop: 3 LDS (phi pair, x_c, x_blank), 3 log-add-exp, 1 STG.64
                 const float2 *php = ph_row + tt;
                 const float *xcp = xt + tt * pitch + col;
-                const float *xbp = kGather ? (xb_g + tt) : (xt + tt * pitch + E2E_CTC_BLANK);
-                const int xb_step = kGather ? 1 : pitch;
-                float2 *outp = rout + (long long)(t0 + tt) * LU;
+                if (!psi_role) {
+                    // state thread: 3 LDS, 2 log-add-exp, 1 STG.64 per frame
+                    const float *xbp = kGather ? (xb_g + tt) : (xt + tt * pitch + E2E_CTC_BLANK);
+                    const int xb_step = kGather ? 1 : pitch;
+                    float2 *outp = rout + (long long)(t0 + tt) * LU;
 #pragma unroll 4
-                for (; tt < rows; ++tt) {
-                    const float2 ph = *php;
-                    const float phi = special ? ph.y : ph.x;
-                    const float xc = *xcp;
-                    const float xb = *xbp;
-                    const float nnb = __fadd_rn(logaddexp<kMath>(nb, phi, lut), xc);
-                    const float nbl = __fadd_rn(logaddexp<kMath>(bl, nb, lut), xb);
-                    psi = logaddexp<kMath>(psi, __fadd_rn(phi, xc), lut);
-                    nb = nnb; bl = nbl;
-                    *outp = make_float2(nnb, nbl);
-                    ++php; xcp += pitch; xbp += xb_step; outp += LU;
+                    for (; tt < rows; ++tt) {
+                        const float2 ph = *php;
+                        const float phi = special ? ph.y : ph.x;
+                        const float nnb = __fadd_rn(logaddexp<kMath>(nb, phi, lut), *xcp);
+                        const float nbl = __fadd_rn(logaddexp<kMath>(bl, nb, lut), *xbp);
+                        nb = nnb; bl = nbl;
+                        *outp = make_float2(nnb, nbl);
+                        ++php; xcp += pitch; xbp += xb_step; outp += LU;
+                    }
+                } else {
+                    // psi thread: 2 LDS, 1 log-add-exp per frame
+#pragma unroll 4
+                    for (; tt < rows; ++tt) {
+                        const float2 ph = *php;
+                        const float phi = special ? ph.y : ph.x;
+                        psi = logaddexp<kMath>(psi, __fadd_rn(phi, *xcp), lut);
+                        ++php; xcp += pitch;
+                    }
                 }
             }
-            __syncthreads();
-            if (!kGather && tid < 32 && k + 2 < n_tiles) issue_rows(k + 2);
+            if (k + 1 < n_tiles) phi_store(k + 1, pf);         // other phi buffer: nobody reads it before the next barrier
         }
     }
 
     if (run) {
-        if (!full && tok == E2E_CTC_EOS) {       // P(<eos> | g) = P(g)   (src/ctc.py:106-107)
+        const bool eos_lane = !full && tok == E2E_CTC_EOS;       // P(<eos> | g) = P(g)   (src/ctc.py:106-107)
+        if (eos_lane && (psi_role || (start >= T && fill_dead))) {
             const float2 a = __ldg(rprev_u + (long long)(T - 1) * p.lanes_prev + s_plane[h - h_lo]);
             psi = logaddexp<kMath>(a.x, a.y, lut);
             // psi aliases r[start-1,0,:] in the reference when the time loop never runs (src/ctc.py:85)
-            if (start >= T && fill_dead) rout[(long long)(start - 1) * LU] = make_float2(psi, E2E_CTC_LOGZERO);
+            if (!psi_role) rout[(long long)(start - 1) * LU] = make_float2(psi, E2E_CTC_LOGZERO);
         }
-        p.psi[(long long)n * C + j] = psi;
-    } else if (active) {
+        if (psi_role) p.psi[(long long)n * C + j] = psi;
+    } else if (active && psi_role) {
         p.psi[(long long)n * C + j] = E2E_CTC_LOGZERO;
     }
 }
 
-static size_t prefix_smem_bytes(bool gather, int nt, int Vp, int H)
+static size_t prefix_smem_bytes(bool gather, int lanes, int Vp, int H)
 {
-    size_t xs_floats = gather ? (size_t)kTile * nt + kTile : (size_t)2 * kTile * Vp;
-    xs_floats = (xs_floats + 3) & ~(size_t)3;
-    // xs | phis | s_plane[H] | s_red[2] (+pad) | bars[2] | LUT replicas.  xs and phis are multiples of 16 bytes and
-    // 4H + 8 (+4 if H is odd) + 16 is a multiple of 8, so one more 8-byte pad makes the LUT 16-byte aligned when needed.
-    size_t b = xs_floats * 4 + (size_t)H * kTile * 8 + (size_t)H * 4 + 8 + ((H & 1) ? 4 : 0) + 16;
-    b += (size_t)kLutNodes * kLutCopies * 16 + 16;
+    size_t b = kLutBytes + prefix_xs_bytes(gather, lanes, Vp) + prefix_phis_bytes(H);
+    b = ((b + (size_t)(H + 2) * 4 + 7) & ~(size_t)7) + 16;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -248,11 +302,11 @@ extern "C" int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int
         return set_error(E2E_ERR_ARG, "e2e_ctc_prefix_score: misaligned buffer");
 
     const long long LU = (long long)B * C;
-    int nt = (int)((LU + 31) / 32 * 32);
-    if (nt > kMaxThreads) {
+    int nl = (int)((LU + 31) / 32 * 32);
+    if (nl > kMaxLanes) {
         // split the utterance's lanes over several CTAs of equal, warp-multiple size
-        const int chunks = (int)((LU + kMaxThreads - 1) / kMaxThreads);
-        nt = (int)(((LU + chunks - 1) / chunks + 31) / 32 * 32);
+        const int chunks = (int)((LU + kMaxLanes - 1) / kMaxLanes);
+        nl = (int)(((LU + chunks - 1) / chunks + 31) / 32 * 32);
     }
     PrefixParams p;
     p.x = x; p.Tmax = Tmax; p.U = U; p.Vp = Vp; p.V = V; p.enc_len = enc_len;
@@ -260,15 +314,16 @@ extern "C" int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int
     p.prev_lane = prev_lane; p.last_tok = last_tok; p.prefix_len = prefix_len; p.n_live = n_live; p.cand = cand;
     p.B = B; p.C = C; p.flags = flags;
     p.psi = psi; p.r_out = reinterpret_cast<float2 *>(r_out); p.status = status;
-    p.chunks_per_utt = (int)((LU + nt - 1) / nt);
-    p.hyps_per_cta = (nt + C - 1) / C + 1;
+    p.lanes_per_cta = nl;
+    p.chunks_per_utt = (int)((LU + nl - 1) / nl);
+    p.hyps_per_cta = (nl + C - 1) / C + 1;
     if (p.hyps_per_cta > B) p.hyps_per_cta = B;
     const long long grid = (long long)U * p.chunks_per_utt;
     if (grid > 0x7fffffffLL) return set_error(E2E_ERR_UNSUPPORTED, "e2e_ctc_prefix_score: grid too large");
 
     const bool gather = Vp > kMaxRowFloats;
     const int math = (flags & E2E_PREFIX_FAST_MATH) ? kMathMufu : ((flags & E2E_PREFIX_LIBM_MATH) ? kMathLibm : kMathLut);
-    const size_t smem = prefix_smem_bytes(gather, nt, Vp, p.hyps_per_cta);
+    const size_t smem = prefix_smem_bytes(gather, nl, Vp, p.hyps_per_cta);
     void (*kern)(PrefixParams);
     if (gather)
         kern = math == kMathLut ? prefix_score_kernel<true, kMathLut>
@@ -281,7 +336,7 @@ extern "C" int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(E2E_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    kern<<<(unsigned)grid, nt, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    kern<<<(unsigned)grid, 2 * nl, smem, static_cast<cudaStream_t>(stream)>>>(p);
     count_launch();
     return check_launch("e2e_ctc_prefix_score");
 }

@@ -220,8 +220,6 @@ class BeamDecoder(nn.Module):
             if s & L.STATUS_TOKEN_NOT_CAND:
                 raise ValueError("utterance %d: beam winner is not in the CTC candidate list "
                                  "(src/decode.py:252: x is not in list)" % u)
-            if s & L.STATUS_FINISHED_OVERFLOW:
-                raise L.E2EError("utterance %d: finished-hypothesis buffer overflow" % u)
 
 
 def nbest_from_arrays(tok, sc, ln, avg, n):

@@ -113,7 +113,7 @@ class BeamBuffers:
         self.parent_slot = z(u, b)
         self.hist_tok, self.hist_parent = z(self.S, u, b), z(self.S, u, b)
         self.hist_score = z(self.S, u, b, dt=F32)
-        self.fin_cap = int(fin_cap if fin_cap is not None else min(b * self.S, 64 + 4 * b))
+        self.fin_cap = int(fin_cap if fin_cap is not None else b)      # best-B closed hypotheses suffice
         self.fin_count = z(u)
         self.fin_step, self.fin_parent = z(u, self.fin_cap), z(u, self.fin_cap)
         self.fin_sum, self.fin_score = z(u, self.fin_cap, dt=F32), z(u, self.fin_cap, dt=F32)

@@ -49,7 +49,6 @@ extern "C" {
 /* bits of the per-utterance status words */
 #define E2E_STATUS_PREFIX_TOO_LONG   1 /* len(prefix) > T: reference raises IndexError, src/ctc.py:85          */
 #define E2E_STATUS_TOKEN_NOT_CAND    2 /* beam winner outside the CTC candidates: ValueError, src/decode.py:252 */
-#define E2E_STATUS_FINISHED_OVERFLOW 4 /* more closed hypotheses than the caller's finished-list capacity       */
 
 /* flags of e2e_ctc_prefix_score */
 #define E2E_PREFIX_FULL           1 /* full_compute semantics (src/ctc.py:29-66): candidates are 0..V-1 */
@@ -126,7 +125,8 @@ int e2e_beam_candidates(const float *att_logits, int ld, int U, int B, int V, in
  *   parent_slot [U][B]  slot of each new hypothesis' parent (identity for idle utterances) — the
  *                       caller gathers decoder / LM / attention states with it
  *   hist_tok, hist_parent (int32) and hist_score (fp32): row `step` of [Smax][U][B]
- * Closed (<eos>-terminated) hypotheses are appended per utterance:
+ * Closed (<eos>-terminated) hypotheses are kept per utterance, stably sorted by mean score and
+ * truncated to the best fin_cap (>= B, so nothing the final selection could return is lost):
  *   fin_count [U]; fin_step, fin_parent (int32), fin_sum, fin_score (fp32): [U][fin_cap]
  * Utterances with step >= max_len[u] are left untouched.
  *   lm_logits may be NULL iff E2E_BEAM_USE_LM is clear; cand/psi iff E2E_BEAM_USE_CTC is clear. */
