@@ -93,10 +93,10 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------
-def workload_lengths(world):
+def workload_lengths(world, n_utts=N_UTTS):
     from e2e_asr_pytorch_b200 import synth
     # replica r uses the same length distribution with its own seed (cfg5: "8 x 2620 utts")
-    return np.concatenate([synth.devclean_lengths(N_UTTS, seed=2 + r) for r in range(world)])
+    return np.concatenate([synth.devclean_lengths(n_utts, seed=2 + r) for r in range(world)])
 
 
 def build_models(device):
@@ -141,7 +141,7 @@ def run_b200(args):
     dec.fast_math = bool(args.fast_math)
     dec.skip_dead_rows = not args.write_dead_rows
     dec.profile_prefix = True
-    lengths = workload_lengths(world)
+    lengths = workload_lengths(world, args.n_utts)
     n_total = len(lengths)
     shards = shard.plan_shards(lengths, world, MAX_RATIO)
     batches = shard.make_batches(shards[rank], lengths, args.max_utts, args.max_padded_frames)
@@ -219,7 +219,7 @@ def run_b200(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg2: char V=31 VGG+BLSTM CTC-attention (librispeech_asr.yaml dims, vgg=1) + 4x1024 RNNLM, "
-                               "beam 8, ctc 0.5, lm 0.5, max_len_ratio 0.2, %d utts/GPU dev-clean-like lengths, random init" % N_UTTS,
+                               "beam 8, ctc 0.5, lm 0.5, max_len_ratio 0.2, %d utts/GPU dev-clean-like lengths, random init" % args.n_utts,
                    "utterances": n_total, "batches_per_gpu": len(batches), "max_utts_per_batch": args.max_utts,
                    "prefix_fast_math": bool(args.fast_math), "skip_dead_rows": not args.write_dead_rows,
                    "l2": "inputs (%.1f GB features + GB-scale prefix states per batch) exceed the 126 MB L2; no flush needed" % (in_bytes / 1e9),
@@ -337,6 +337,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-utts", type=int, default=N_UTTS, help="utterances per GPU (profiling runs only; the metric is quoted on 2620)")
     ap.add_argument("--max-utts", type=int, default=1024)
     ap.add_argument("--max-padded-frames", type=int, default=700000)
     ap.add_argument("--fast-math", type=int, default=0)

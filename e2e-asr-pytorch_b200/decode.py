@@ -117,6 +117,8 @@ class BeamDecoder(nn.Module):
         self.skip_dead_rows = True      # do not write state rows t < len(prefix) nobody reads back
         self.profile_prefix = False     # bench.py: CUDA-event pair around every prefix-score launch
         self.prefix_events = []         # (start, end, cand_frames [SURVEY §8d formula], cand_frames actually computed)
+        self.profile_phases = False     # tools/profile_phases.py: CUDA-event time per phase of decode_batch
+        self.phase_ms = {}
         self.last_stats = {}
 
     def create_msg(self):
@@ -153,9 +155,19 @@ class BeamDecoder(nn.Module):
         min_len = torch.tensor([int(np.ceil(int(l) * self.min_len_ratio)) for l in lens_cpu], dtype=torch.int32)
         n_steps = int(max_len.max()) if n_utts else 0
 
+        marks = []
+
+        def mark(name):
+            if self.profile_phases:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
         with _Fp32Math():
+            mark("start")
             stepper = BatchedStepper(self.asr, self.lm if self.apply_lm else None)
             enc, enc_len = stepper.encode(audio_feature, feature_len.to(dev))
+            mark("encode")
             enc_len32 = enc_len.to(torch.int32).contiguous()
             stepper.start(enc, enc_len, beam)
             t_max = enc.shape[1]
@@ -172,8 +184,10 @@ class BeamDecoder(nn.Module):
             if self.profile_prefix and self.apply_ctc:
                 t_np, s_np = enc_len.cpu().numpy().astype(np.int64), max_len.numpy().astype(np.int64)
 
+            mark("ctc_posterior")
             for step in range(n_steps):                                            # decode.py:104
                 att_logits, lm_logits = stepper.step(buf.last_tok.view(-1).long())
+                mark("model_step")
                 ops.beam_candidates(att_logits, n_utts, beam, vocab, n_cand, buf.n_active, buf.att_stats, buf.cand)
                 if self.apply_ctc:
                     r_cur = r_a if (step % 2 == 0) else r_b
@@ -191,12 +205,19 @@ class BeamDecoder(nn.Module):
                                                    float(hyps * np.maximum(t_np[act] - max(1, step), 0).sum())))
                     r_prev = r_cur
                 ops.beam_combine_prune(buf, att_logits, lm_logits, vocab, step, ctc_w, lm_w, EOS_THRESHOLD)
+                mark("beam_kernels")
                 stepper.reorder(buf.parent_slot)
+                mark("reorder")
 
             tok, sc, ln, avg, n = ops.beam_finalize(buf)
+            mark("finalize")
             status = buf.status.cpu()
             tok, sc, ln, avg, n = tok.cpu(), sc.cpu(), ln.cpu(), avg.cpu(), n.cpu()
 
+        if self.profile_phases:
+            torch.cuda.synchronize()
+            for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+                self.phase_ms[name] = self.phase_ms.get(name, 0.0) + a.elapsed_time(b)
         self._raise_like_reference(status, n, max_len)
         enc_len_cpu = enc_len.cpu()
         self.last_stats = {
