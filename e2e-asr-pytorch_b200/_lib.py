@@ -34,7 +34,7 @@ SIGNATURES = {
                                      c_void_p, c_int,
                                      c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_int, c_int, c_int,
-                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "e2e_beam_candidates": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "e2e_beam_combine_prune": (c_int, [c_void_p, c_int, c_void_p,
                                        c_void_p, c_int,
@@ -47,7 +47,9 @@ SIGNATURES = {
                                        c_void_p,
                                        c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                       c_int, c_void_p, c_void_p]),
+                                       c_int, c_void_p, c_int, c_void_p]),
+    "e2e_attention_loc_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
+                                       c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "e2e_beam_finalize": (c_int, [c_int, c_int, c_void_p,
                                   c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p,

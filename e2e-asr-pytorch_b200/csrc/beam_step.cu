@@ -383,7 +383,7 @@ extern "C" int e2e_beam_combine_prune(const float *att_logits, int ld_att, const
                                       int *parent_slot,
                                       int *hist_tok, int *hist_parent, float *hist_score,
                                       int *fin_count, int *fin_step, int *fin_parent, float *fin_sum, float *fin_score,
-                                      int fin_cap, int *status, void *stream)
+                                      int fin_cap, int *status, int n_run, void *stream)
 {
     using namespace e2e;
     const bool use_ctc = (flags & E2E_BEAM_USE_CTC) != 0, use_lm = (flags & E2E_BEAM_USE_LM) != 0;
@@ -411,7 +411,8 @@ extern "C" int e2e_beam_combine_prune(const float *att_logits, int ld_att, const
         cudaError_t e = cudaFuncSetAttribute(beam_combine_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(E2E_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    beam_combine_prune_kernel<<<U, B * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    if (n_run <= 0 || n_run > U) n_run = U;
+    beam_combine_prune_kernel<<<n_run, B * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
     count_launch();
     return check_launch("e2e_beam_combine_prune");
 }

@@ -288,7 +288,7 @@ extern "C" int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int
                                     const float *r_prev, int lanes_prev,
                                     const int *prev_lane, const int *last_tok, const int *prefix_len,
                                     const int *n_live, const int *cand, int B, int C, int flags,
-                                    float *psi, float *r_out, int *status, void *stream)
+                                    float *psi, float *r_out, int *status, int n_run, void *stream)
 {
     using namespace e2e;
     const bool full = (flags & E2E_PREFIX_FULL) != 0;
@@ -318,7 +318,8 @@ extern "C" int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int
     p.chunks_per_utt = (int)((LU + nl - 1) / nl);
     p.hyps_per_cta = (nl + C - 1) / C + 1;
     if (p.hyps_per_cta > B) p.hyps_per_cta = B;
-    const long long grid = (long long)U * p.chunks_per_utt;
+    if (n_run <= 0 || n_run > U) n_run = U;      // only the first n_run utterances are processed
+    const long long grid = (long long)n_run * p.chunks_per_utt;
     if (grid > 0x7fffffffLL) return set_error(E2E_ERR_UNSUPPORTED, "e2e_ctc_prefix_score: grid too large");
 
     const bool gather = Vp > kMaxRowFloats;

@@ -68,15 +68,19 @@ class Hypothesis:
 
 
 class _Fp32Math:
-    """The reference computes in fp32 on the CPU; keep cuBLAS/cuDNN out of TF32."""
+    """The reference computes in fp32 on the CPU: keep cuBLAS/cuDNN out of TF32 and keep the
+    bf16 split GEMMs (stepper.SplitLinear) on full fp32 accumulation."""
 
     def __enter__(self):
-        self.prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
-        torch.backends.cuda.matmul.allow_tf32 = False
+        mm = torch.backends.cuda.matmul
+        self.prev = (mm.allow_tf32, torch.backends.cudnn.allow_tf32, mm.allow_bf16_reduced_precision_reduction)
+        mm.allow_tf32 = False
         torch.backends.cudnn.allow_tf32 = False
+        mm.allow_bf16_reduced_precision_reduction = False
 
     def __exit__(self, *exc):
-        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = self.prev
+        mm = torch.backends.cuda.matmul
+        mm.allow_tf32, torch.backends.cudnn.allow_tf32, mm.allow_bf16_reduced_precision_reduction = self.prev
 
 
 class BeamDecoder(nn.Module):
@@ -115,11 +119,20 @@ class BeamDecoder(nn.Module):
         # knobs of the device path (not part of the reference interface)
         self.fast_math = False          # MUFU log-add-exp in the prefix-score kernel
         self.skip_dead_rows = True      # do not write state rows t < len(prefix) nobody reads back
+        self.split_gemm = True          # fp32-accurate 3-way bf16 split of the recurrent GEMMs (stepper.py)
+        self.fused_attention = True     # hand-written location-aware attention kernel (csrc/attention_step.cu)
+        self._stepper = None            # (device, split_gemm, stepper): weights are split once per device
         self.profile_prefix = False     # bench.py: CUDA-event pair around every prefix-score launch
         self.prefix_events = []         # (start, end, cand_frames [SURVEY §8d formula], cand_frames actually computed)
         self.profile_phases = False     # tools/profile_phases.py: CUDA-event time per phase of decode_batch
         self.phase_ms = {}
         self.last_stats = {}
+
+    def __getstate__(self):
+        # bin/test_asr.py:108,138 deep-copies and pickles the decoder: drop the per-device caches
+        d = self.__dict__.copy()
+        d["_stepper"], d["prefix_events"] = None, []
+        return d
 
     def create_msg(self):
         msg = ['Decode spec| Beam size = {}\t| Min/Max len ratio = {}/{}'.format(
@@ -151,9 +164,19 @@ class BeamDecoder(nn.Module):
         lm_w = self.lm_w if self.apply_lm else 0.0
         lens_cpu = feature_len.detach().cpu().long()
         # decode.py:74-78: output length limits come from the INPUT length
-        max_len = torch.tensor([int(np.ceil(int(l) * self.max_len_ratio)) for l in lens_cpu], dtype=torch.int32)
-        min_len = torch.tensor([int(np.ceil(int(l) * self.min_len_ratio)) for l in lens_cpu], dtype=torch.int32)
+        max_np = np.array([int(np.ceil(int(l) * self.max_len_ratio)) for l in lens_cpu], dtype=np.int64)
+        min_np = np.array([int(np.ceil(int(l) * self.min_len_ratio)) for l in lens_cpu], dtype=np.int64)
+        # Longest first: the utterances still decoding at any step are then a prefix of the batch,
+        # and every kernel / model step only visits that prefix.
+        order = np.lexsort((np.arange(n_utts), -max_np)) if n_utts else np.zeros(0, dtype=np.int64)
+        inverse = np.argsort(order)
+        if n_utts and not np.array_equal(order, np.arange(n_utts)):
+            sel = torch.as_tensor(order, device=dev)
+            audio_feature, feature_len = audio_feature.index_select(0, sel), feature_len.to(dev).index_select(0, sel)
+        max_len = torch.as_tensor(max_np[order], dtype=torch.int32)
+        min_len = torch.as_tensor(min_np[order], dtype=torch.int32)
         n_steps = int(max_len.max()) if n_utts else 0
+        n_run = [int((max_np > s).sum()) for s in range(n_steps)]      # live utterances per step
 
         marks = []
 
@@ -165,7 +188,12 @@ class BeamDecoder(nn.Module):
 
         with _Fp32Math():
             mark("start")
-            stepper = BatchedStepper(self.asr, self.lm if self.apply_lm else None)
+            knobs = (self.split_gemm, self.fused_attention)
+            if self._stepper is None or self._stepper[0] != dev or self._stepper[1] != knobs:
+                self._stepper = (dev, knobs, BatchedStepper(self.asr, self.lm if self.apply_lm else None,
+                                                            self.split_gemm, self.fused_attention))
+            stepper = self._stepper[2]
+            stepper.mark = mark
             enc, enc_len = stepper.encode(audio_feature, feature_len.to(dev))
             mark("encode")
             enc_len32 = enc_len.to(torch.int32).contiguous()
@@ -186,9 +214,10 @@ class BeamDecoder(nn.Module):
 
             mark("ctc_posterior")
             for step in range(n_steps):                                            # decode.py:104
-                att_logits, lm_logits = stepper.step(buf.last_tok.view(-1).long())
-                mark("model_step")
-                ops.beam_candidates(att_logits, n_utts, beam, vocab, n_cand, buf.n_active, buf.att_stats, buf.cand)
+                k = n_run[step]
+                att_logits, lm_logits = stepper.step(buf.last_tok[:k].reshape(-1).long(), k)
+                mark("step_rest")
+                ops.beam_candidates(att_logits, k, beam, vocab, n_cand, buf.n_active, buf.att_stats, buf.cand)
                 if self.apply_ctc:
                     r_cur = r_a if (step % 2 == 0) else r_b
                     if self.profile_prefix:
@@ -196,7 +225,7 @@ class BeamDecoder(nn.Module):
                         ev0.record()
                     ops.ctc_prefix_score(x, vocab, enc_len32, r_prev, buf.prev_lane.view(-1), buf.last_tok.view(-1),
                                          buf.prefix_len.view(-1), buf.n_active, buf.cand, beam, n_cand, pflags,
-                                         psi=buf.psi, r_out=r_cur, status=buf.status)
+                                         psi=buf.psi, r_out=r_cur, status=buf.status, n_run=k)
                     if self.profile_prefix:
                         ev1.record()
                         act = s_np > step                     # utterances that still decode at this step
@@ -204,7 +233,7 @@ class BeamDecoder(nn.Module):
                         self.prefix_events.append((ev0, ev1, float(hyps * t_np[act].sum()),
                                                    float(hyps * np.maximum(t_np[act] - max(1, step), 0).sum())))
                     r_prev = r_cur
-                ops.beam_combine_prune(buf, att_logits, lm_logits, vocab, step, ctc_w, lm_w, EOS_THRESHOLD)
+                ops.beam_combine_prune(buf, att_logits, lm_logits, vocab, step, ctc_w, lm_w, EOS_THRESHOLD, n_run=k)
                 mark("beam_kernels")
                 stepper.reorder(buf.parent_slot)
                 mark("reorder")
@@ -212,14 +241,17 @@ class BeamDecoder(nn.Module):
             tok, sc, ln, avg, n = ops.beam_finalize(buf)
             mark("finalize")
             status = buf.status.cpu()
-            tok, sc, ln, avg, n = tok.cpu(), sc.cpu(), ln.cpu(), avg.cpu(), n.cpu()
+            inv = torch.as_tensor(inverse, device=dev)
+            tok, sc, ln, avg, n = (a.index_select(0, inv).cpu() for a in (tok, sc, ln, avg, n))
+            status = status[torch.as_tensor(inverse)]
 
         if self.profile_phases:
             torch.cuda.synchronize()
             for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
                 self.phase_ms[name] = self.phase_ms.get(name, 0.0) + a.elapsed_time(b)
         self._raise_like_reference(status, n, max_len)
-        enc_len_cpu = enc_len.cpu()
+        enc_len_cpu = enc_len.cpu()[torch.as_tensor(inverse)]
+        max_len = max_len[torch.as_tensor(inverse)]
         self.last_stats = {
             "utterances": n_utts, "steps": n_steps, "enc_frames": [int(t) for t in enc_len_cpu],
             # unit count of SURVEY.md §8d: sum_s H_s * C * T per utterance

@@ -154,14 +154,32 @@ class RecurrentLayer(nn.Module):
         out, _ = self.layer(x)                      # reference runs the padded batch unpacked
         return self._post(out, x_len)
 
-    def forward_packed(self, x, x_len):
-        """Ragged batch: pack so that the backward direction of every utterance
-        starts at its own last frame (== what a batch-1 call computes)."""
-        t_max = x.shape[1]
-        packed = nn.utils.rnn.pack_padded_sequence(x, x_len.cpu().clamp(min=1), batch_first=True, enforce_sorted=False)
-        out, _ = self.layer(packed)
-        out, _ = nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=t_max)
-        return self._post(out, x_len)
+    def forward_ragged(self, x, x_len):
+        """Zero-padded batch of utterances of different lengths, per-utterance results equal to
+        batch-1 calls for every frame t < x_len — without packed sequences (cuDNN runs packed
+        input one time step per kernel).  The forward direction of a padded row is already exact
+        on its valid frames; the backward direction is run as a forward pass over each row
+        reversed in place within its own length."""
+        rnn = self.layer
+        if not rnn.bidirectional:
+            out, _ = rnn(x)
+            return self._post(out, x_len)
+        n, t, _ = x.shape
+        fn = torch._VF.lstm if isinstance(rnn, nn.LSTM) else torch._VF.gru
+        zeros = x.new_zeros(1, n, rnn.hidden_size)
+        hx = (zeros, zeros) if isinstance(rnn, nn.LSTM) else zeros
+        names = ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")
+        w_fw = [getattr(rnn, k) for k in names]
+        w_bw = [getattr(rnn, k + "_reverse") for k in names]
+        ar = torch.arange(t, device=x.device)[None, :]
+        ln = x_len.to(x.device).clamp(min=1)[:, None]
+        rev = torch.where(ar < ln, ln - 1 - ar, ar)                      # [n, t] own-length reversal, padding stays put
+        gather = rev[:, :, None]
+        fw = fn(x, hx, w_fw, True, 1, 0.0, False, False, True)[0]
+        x_rev = x.gather(1, gather.expand(n, t, x.shape[2]))
+        bw = fn(x_rev, hx, w_bw, True, 1, 0.0, False, False, True)[0]
+        bw = bw.gather(1, gather.expand(n, t, bw.shape[2]))
+        return self._post(torch.cat([fw, bw], dim=-1), x_len)
 
 
 class Encoder(nn.Module):
@@ -198,12 +216,12 @@ class Encoder(nn.Module):
     def forward_ragged(self, x, x_len):
         """Batched encode of zero-padded utterances of different lengths with
         per-utterance results equal (up to library kernel selection) to
-        batch-1 calls: masked VGG + packed recurrent layers."""
+        batch-1 calls: masked VGG + per-row reversed recurrent layers."""
         for layer in self.layers:
             if isinstance(layer, VGGFrontEnd):
                 x, x_len = layer.forward_masked(x, x_len)
             else:
-                x, x_len = layer.forward_packed(x, x_len)
+                x, x_len = layer.forward_ragged(x, x_len)
         return x, x_len
 
 

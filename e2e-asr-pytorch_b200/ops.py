@@ -57,7 +57,7 @@ def ctc_init_state(x, enc_len=None, out=None):
 
 
 def ctc_prefix_score(x, vocab, enc_len, r_prev, prev_lane, last_tok, prefix_len, n_live, cand,
-                     beam, n_cand, flags=0, psi=None, r_out=None, status=None):
+                     beam, n_cand, flags=0, psi=None, r_out=None, status=None, n_run=0):
     """One launch of the prefix-score kernel; see e2e_ctc_prefix_score in the header."""
     t, u, vp = x.shape
     _chk(x, F32, "x")
@@ -82,7 +82,7 @@ def ctc_prefix_score(x, vocab, enc_len, r_prev, prev_lane, last_tok, prefix_len,
     L.check(L.load().e2e_ctc_prefix_score(
         L.ptr(x), t, u, vp, int(vocab), L.ptr(enc_len), L.ptr(r_prev), lanes_prev,
         L.ptr(prev_lane), L.ptr(last_tok), L.ptr(prefix_len), L.ptr(n_live), L.ptr(cand),
-        int(beam), int(n_cand), int(flags), L.ptr(psi), L.ptr(r_out), L.ptr(status), _stream()))
+        int(beam), int(n_cand), int(flags), L.ptr(psi), L.ptr(r_out), L.ptr(status), int(n_run), _stream()))
     return psi, r_out
 
 
@@ -123,7 +123,7 @@ class BeamBuffers:
         self.psi = z(u * b, max(1, n_cand), dt=F32)
 
 
-def beam_combine_prune(buf, att_logits, lm_logits, vocab, step, ctc_weight, lm_weight, eos_threshold=1.5):
+def beam_combine_prune(buf, att_logits, lm_logits, vocab, step, ctc_weight, lm_weight, eos_threshold=1.5, n_run=0):
     """One decode step of score combine + eos threshold + top-k + prune for all utterances."""
     _chk(att_logits, F32, "att_logits")
     _chk(lm_logits, F32, "lm_logits")
@@ -140,7 +140,7 @@ def beam_combine_prune(buf, att_logits, lm_logits, vocab, step, ctc_weight, lm_w
         L.ptr(buf.parent_slot),
         L.ptr(buf.hist_tok), L.ptr(buf.hist_parent), L.ptr(buf.hist_score),
         L.ptr(buf.fin_count), L.ptr(buf.fin_step), L.ptr(buf.fin_parent), L.ptr(buf.fin_sum), L.ptr(buf.fin_score),
-        buf.fin_cap, L.ptr(buf.status), _stream()))
+        buf.fin_cap, L.ptr(buf.status), int(n_run), _stream()))
 
 
 def beam_finalize(buf, out_cap=None):
@@ -158,6 +158,22 @@ def beam_finalize(buf, out_cap=None):
         L.ptr(buf.fin_count), L.ptr(buf.fin_step), L.ptr(buf.fin_parent), L.ptr(buf.fin_sum), L.ptr(buf.fin_score),
         buf.fin_cap, L.ptr(tok), L.ptr(sc), L.ptr(ln), L.ptr(avg), L.ptr(n), cap, _stream()))
     return tok, sc, ln, avg, n
+
+
+def attention_loc_step(key, query, loc_feat, enc_len, w_proj, w_energy, b_energy, temperature, beam, out=None):
+    """Fused location-aware attention energies + masked softmax: key [U,T,A], query [n,A],
+    loc_feat [n,K,T] (conv of the previous alignment) -> attn [n,T]."""
+    for t, nm in ((key, "key"), (query, "query"), (loc_feat, "loc_feat"), (w_proj, "w_proj"), (w_energy, "w_energy")):
+        _chk(t, F32, nm)
+    _chk(enc_len, I32, "enc_len")
+    n, k, t_len = loc_feat.shape
+    a = key.shape[2]
+    attn = out if out is not None else torch.empty((n, t_len), dtype=F32, device=key.device)
+    _chk(attn, F32, "attn", n * t_len)
+    L.check(L.load().e2e_attention_loc_step(L.ptr(key), L.ptr(query), L.ptr(loc_feat), L.ptr(enc_len), L.ptr(w_proj),
+                                           L.ptr(w_energy), float(b_energy), float(temperature), int(n), int(beam),
+                                           int(t_len), int(a), int(k), L.ptr(attn), _stream()))
+    return attn
 
 
 def launch_count():

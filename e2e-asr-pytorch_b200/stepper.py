@@ -13,71 +13,129 @@ per decode step over all N = U*B hypotheses with device-resident states:
 The stepper reads the weights straight out of the ``asr`` / ``lm`` modules it is
 given (parameter names of the reference), so it works with the reference's own
 objects as well as with ``model.py``.
+
+Two things keep the library GEMMs off the critical path without leaving fp32:
+
+* utterances arrive sorted by decreasing length, so the ones still decoding are
+  always a PREFIX of the batch; every step only touches the first ``k`` of them;
+* ``split_gemm``: the recurrent GEMMs ([N,2048]x[2048,4096] per LM layer) run on
+  the tensor cores as a 3-way bf16 split of both operands (6 partial products
+  a1w1+a1w2+a2w1+a1w3+a2w2+a3w1, fp32 accumulation, see SplitLinear).  x = a1+a2+a3
+  is exact for fp32 inputs, the dropped products are below 2^-23 of |a||w|, so
+  the result is as accurate as cuBLAS' fp32 SIMT GEMM (tests/test_gpu_decode.py
+  checks it against fp64) at less than half its time;
+* ``fused_attention``: the location-aware energies + masked softmax run in one
+  hand-written kernel (csrc/attention_step.cu) instead of ~8 passes over
+  [U*B, T, 300] temporaries.
 """
 import numpy as np
 import torch
 import torch.nn.functional as F
 
 
-def _rnn_weights(rnn):
-    ws = []
-    for l in range(rnn.num_layers):
-        ws.append(tuple(getattr(rnn, "{}_l{}".format(k, l)) for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")))
-    return ws
+def _split3(x):
+    """fp32 -> three bf16 tensors with x == a1 + a2 + a3 (exactly, barring underflow)."""
+    a1 = x.to(torch.bfloat16)
+    r = x - a1.float()
+    a2 = r.to(torch.bfloat16)
+    a3 = (r - a2.float()).to(torch.bfloat16)
+    return a1, a2, a3
 
 
-def _lstm_cell(x, h, c, w):
-    w_ih, w_hh, b_ih, b_hh = w
-    gates = F.linear(x, w_ih, b_ih) + F.linear(h, w_hh, b_hh)
-    i, f, g, o = gates.chunk(4, dim=-1)
-    c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
-    return torch.sigmoid(o) * torch.tanh(c2), c2
+class SplitLinear:
+    """y = x @ W^T + b with fp32 accuracy on bf16 tensor cores.
 
+    x = a1+a2+a3 and W = w1+w2+w3 (bf16 pieces).  The six partial products that matter are grouped
+    by magnitude — {a1w1}, {a1w2, a2w1}, {a1w3, a2w2, a3w1} — one GEMM per group (pieces
+    concatenated along K) accumulated smallest group first through the fp32 C operand, because a
+    tensor-core accumulator that mixes magnitudes loses the small terms (measured: 2.8e-4 vs 4.4e-5
+    max error on a 2048-long dot product; cuBLAS fp32 SIMT: 3.7e-5).  Small batches stay on the
+    plain fp32 GEMM, where the split's extra passes do not pay."""
 
-def _gru_cell(x, h, w):
-    w_ih, w_hh, b_ih, b_hh = w
-    gi, gh = F.linear(x, w_ih, b_ih), F.linear(h, w_hh, b_hh)
-    ir, iz, inn = gi.chunk(3, dim=-1)
-    hr, hz, hn = gh.chunk(3, dim=-1)
-    r, z = torch.sigmoid(ir + hr), torch.sigmoid(iz + hz)
-    n = torch.tanh(inn + r * hn)
-    return (1 - z) * n + z * h
+    MIN_ROWS = 1024
+
+    def __init__(self, weight, bias=None):
+        self.weight = weight.detach().float()
+        self.bias = None if bias is None else bias.detach().float()
+        w1, w2, w3 = _split3(self.weight)
+        self.b0 = w1.t().contiguous()                                   # [K, M]
+        self.b1 = torch.cat([w2, w1], dim=1).t().contiguous()           # [2K, M]
+        self.b2 = torch.cat([w3, w2, w1], dim=1).t().contiguous()       # [3K, M]
+
+    def __call__(self, x):
+        if x.shape[0] < self.MIN_ROWS:
+            return F.linear(x, self.weight, self.bias)
+        a1, a2, a3 = _split3(x)
+        y = torch.mm(torch.cat([a1, a2, a3], dim=1), self.b2, out_dtype=torch.float32)
+        y = torch.addmm(y, torch.cat([a1, a2], dim=1), self.b1, out_dtype=torch.float32)
+        y = torch.addmm(y, a1, self.b0, out_dtype=torch.float32)
+        return y if self.bias is None else y + self.bias
 
 
 class _Rnn:
-    """n-layer LSTM/GRU advanced one token at a time for a batch of rows."""
+    """n-layer LSTM/GRU advanced one token at a time for a batch of rows.  States are lists of
+    per-layer [N, D] tensors so that row prefixes are contiguous views."""
 
-    def __init__(self, rnn):
+    def __init__(self, rnn, split_gemm=False, first_input_table=None):
         self.is_lstm = isinstance(rnn, torch.nn.LSTM)
         if not self.is_lstm and not isinstance(rnn, torch.nn.GRU):
             raise NotImplementedError("only LSTM / GRU recurrent layers are supported")
-        self.w = _rnn_weights(rnn)
         self.layers, self.dim = rnn.num_layers, rnn.hidden_size
+        self.split = split_gemm and self.is_lstm
+        self.w, self.fused, self.table0 = [], [], None
+        for l in range(self.layers):
+            w = tuple(getattr(rnn, "{}_l{}".format(k, l)) for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+            self.w.append(w)
+            if not self.split:
+                continue
+            if l == 0 and first_input_table is not None:
+                # layer 0 sees one of V embeddings: its input projection is a [V, 4D] table
+                self.table0 = (first_input_table.double() @ w[0].double().t() + w[2].double()).float()
+                self.fused.append(SplitLinear(w[1], w[3]))
+            else:
+                self.fused.append(SplitLinear(torch.cat([w[0], w[1]], dim=1), w[2] + w[3]))
 
     def zeros(self, n, device):
-        h = torch.zeros(self.layers, n, self.dim, device=device)
-        return (h, torch.zeros_like(h)) if self.is_lstm else (h, None)
+        z = lambda: [torch.zeros(n, self.dim, device=device) for _ in range(self.layers)]
+        return (z(), z() if self.is_lstm else None)
 
-    def step(self, x, state):
+    def step(self, x, state, n, tok=None):
+        """x [n, in] (or token ids for a tabled layer 0), state rows [:n] are used."""
         h, c = state
         hs, cs = [], []
         for l in range(self.layers):
+            hl = h[l][:n]
             if self.is_lstm:
-                x, c2 = _lstm_cell(x, h[l], c[l], self.w[l])
+                if self.split:
+                    if l == 0 and self.table0 is not None:
+                        gates = self.table0.index_select(0, tok) + self.fused[0](hl)
+                    else:
+                        gates = self.fused[l](torch.cat([x, hl], dim=1))
+                else:
+                    w_ih, w_hh, b_ih, b_hh = self.w[l]
+                    gates = F.linear(x, w_ih, b_ih) + F.linear(hl, w_hh, b_hh)
+                i, f, g, o = gates.chunk(4, dim=-1)
+                c2 = torch.sigmoid(f) * c[l][:n] + torch.sigmoid(i) * torch.tanh(g)
+                x = torch.sigmoid(o) * torch.tanh(c2)
                 cs.append(c2)
             else:
-                x = _gru_cell(x, h[l], self.w[l])
+                w_ih, w_hh, b_ih, b_hh = self.w[l]
+                gi, gh = F.linear(x, w_ih, b_ih), F.linear(hl, w_hh, b_hh)
+                ir, iz, inn = gi.chunk(3, dim=-1)
+                hr, hz, hn = gh.chunk(3, dim=-1)
+                r, z = torch.sigmoid(ir + hr), torch.sigmoid(iz + hz)
+                x = (1 - z) * torch.tanh(inn + r * hn) + z * hl
             hs.append(x)
-        return x, (torch.stack(hs), torch.stack(cs) if self.is_lstm else None)
+        return x, (hs, cs if self.is_lstm else None)
 
     @staticmethod
     def gather(state, idx):
         h, c = state
-        return (h.index_select(1, idx), c.index_select(1, idx) if c is not None else None)
+        return ([t.index_select(0, idx) for t in h], [t.index_select(0, idx) for t in c] if c is not None else None)
 
 
 class BatchedStepper:
-    def __init__(self, asr, lm=None):
+    def __init__(self, asr, lm=None, split_gemm=False, fused_attention=False):
         att = asr.attention
         if att.num_head != 1:
             raise NotImplementedError("multi-head attention is not supported by the batched beam search")
@@ -85,8 +143,17 @@ class BatchedStepper:
             raise NotImplementedError("attention mode " + str(att.mode))
         self.asr, self.lm = asr, lm
         self.mode, self.temperature = att.mode, att.att_layer.temperature
-        self.dec = _Rnn(asr.decoder.layers)
-        self.lm_rnn = _Rnn(lm.rnn) if lm is not None else None
+        self.dec = _Rnn(asr.decoder.layers, split_gemm)
+        self.lm_rnn = _Rnn(lm.rnn, split_gemm, lm.emb.weight.detach()) if lm is not None else None
+        self.mark = lambda name: None            # profiling hook (decode.py sets it)
+        self.fused_attention = False
+        if fused_attention and self.mode == "loc":
+            lay = att.att_layer
+            if lay.loc_proj.weight.shape[1] <= 12 and lay.loc_proj.weight.shape[0] % 4 == 0:
+                self.fused_attention = True
+                self._w_proj = lay.loc_proj.weight.detach().contiguous()
+                self._w_energy = lay.gen_energy.weight.detach().reshape(-1).contiguous()
+                self._b_energy = float(lay.gen_energy.bias.detach().reshape(-1)[0])
 
     # -- once per batch ---------------------------------------------------------------------
     def encode(self, feats, lens):
@@ -124,41 +191,57 @@ class BatchedStepper:
             self.prev_att = None
         self.dec_state = self.dec.zeros(self.N, dev)
         self.lm_state = self.lm_rnn.zeros(self.N, dev) if self.lm_rnn is not None else None
+        self._base = torch.arange(u, device=dev, dtype=torch.long)[:, None] * beam
+        self._enc_len32 = enc_len.to(torch.int32).contiguous()
 
     # -- once per decode step ---------------------------------------------------------------
-    def step(self, prev_tok):
-        """prev_tok [N] long -> (att_logits [N,V], lm_logits [N,V] | None); new states are held
-        until :meth:`reorder` commits them in the surviving hypotheses' order."""
+    def step(self, prev_tok, k=None):
+        """Advance the first ``k`` utterances (all by default).  prev_tok [k*B] long ->
+        (att_logits [k*B,V], lm_logits [k*B,V] | None); the new states are held until
+        :meth:`reorder` commits them in the surviving hypotheses' order."""
         asr, att = self.asr, self.asr.attention
-        u, b, t = self.U, self.B, self.T
-        h = self.dec_state[0]
-        query = torch.tanh(att.proj_q(h.transpose(0, 1).reshape(self.N, -1)))     # asr.py:337 / :251-254
-        if self.mode == "loc":
-            lay = att.att_layer
-            loc = lay.loc_conv(self.prev_att[:, None, :]).transpose(1, 2)          # [N,T,K]
-            loc = torch.tanh(lay.loc_proj(loc)).view(u, b, t, -1)
-            mix = torch.tanh(self.key[:, None] + query.view(u, b, 1, -1) + loc)
-            energy = lay.gen_energy(mix).squeeze(-1)                               # [U,B,T]  module.py:1168
+        k = self.U if k is None else k
+        b, t = self.B, self.T
+        n = k * b
+        self._k = k
+        query = torch.tanh(att.proj_q(torch.cat([h[:n] for h in self.dec_state[0]], dim=1)))   # asr.py:337 / :251-254
+        if self.mode == "loc" and self.fused_attention:
+            from . import ops
+            feat = att.att_layer.loc_conv(self.prev_att[:n, None, :]).contiguous()     # [n,K,T]  module.py:1163 (cuDNN)
+            attn = ops.attention_loc_step(self.key, query.contiguous(), feat, self._enc_len32, self._w_proj,
+                                          self._w_energy, self._b_energy, self.temperature, b).view(k, b, t)
         else:
-            energy = torch.bmm(query.view(u, b, -1), self.key.transpose(1, 2))     # module.py:1126
-        score = (energy / self.temperature).masked_fill(self.pad[:, None, :], -np.inf)
-        attn = torch.softmax(score, dim=-1)                                        # [U,B,T]
-        context = torch.bmm(attn, self.value).view(self.N, -1)                     # module.py:1114
+            if self.mode == "loc":
+                lay = att.att_layer
+                loc = lay.loc_conv(self.prev_att[:n, None, :]).transpose(1, 2)         # [n,T,K]
+                loc = torch.tanh(lay.loc_proj(loc)).view(k, b, t, -1)
+                mix = torch.tanh(self.key[:k, None] + query.view(k, b, 1, -1) + loc)
+                energy = lay.gen_energy(mix).squeeze(-1)                               # [k,B,T]  module.py:1168
+            else:
+                energy = torch.bmm(query.view(k, b, -1), self.key[:k].transpose(1, 2))  # module.py:1126
+            score = (energy / self.temperature).masked_fill(self.pad[:k, None, :], -np.inf)
+            attn = torch.softmax(score, dim=-1)                                        # [k,B,T]
+        context = torch.bmm(attn, self.value[:k]).view(n, -1)                      # module.py:1114
+        self.mark("step_attention")
         dec_in = torch.cat([asr.pre_embed(prev_tok), context], dim=-1)             # decode.py:114-115
-        top, self._new_dec = self.dec.step(dec_in, self.dec_state)
+        top, self._new_dec = self.dec.step(dec_in, self.dec_state, n)
         att_logits = asr.decoder.char_trans(top)                                   # asr.py:265
-        self._new_att = attn.view(self.N, t) if self.mode == "loc" else None
+        self._new_att = attn.view(n, t) if self.mode == "loc" else None
+        self.mark("step_speller")
         lm_logits = None
         if self.lm is not None:
-            top, self._new_lm = self.lm_rnn.step(self.lm.emb(prev_tok), self.lm_state)
+            x0 = None if self.lm_rnn.table0 is not None else self.lm.emb(prev_tok)
+            top, self._new_lm = self.lm_rnn.step(x0, self.lm_state, n, tok=prev_tok)
             lm_logits = F.linear(top, self.lm.emb.weight) if self.lm.emb_tying else self.lm.trans(top)   # lm.py:33-37
+            self.mark("step_lm")
         return att_logits.contiguous(), (lm_logits.contiguous() if lm_logits is not None else None)
 
     def reorder(self, parent_slot):
         """parent_slot [U,B] int32 (slot of each survivor's parent): children inherit the
-        post-step states of their parent (decode.py:159-162,250-257)."""
-        base = torch.arange(self.U, device=parent_slot.device, dtype=torch.long)[:, None] * self.B
-        idx = (base + parent_slot.long()).reshape(-1)
+        post-step states of their parent (decode.py:159-162,250-257).  Only the rows of the
+        utterances advanced by the last :meth:`step` are touched."""
+        k = self._k
+        idx = (self._base[:k] + parent_slot[:k].long()).reshape(-1)
         self.dec_state = _Rnn.gather(self._new_dec, idx)
         if self._new_att is not None:
             self.prev_att = self._new_att.index_select(0, idx)

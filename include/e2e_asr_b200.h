@@ -96,12 +96,15 @@ int e2e_ctc_init_state(const float *x, int Tmax, int U, int Vp, const int *enc_l
  *   psi        [U*B][C]            out: prefix log-probabilities
  *   r_out      [U][Tmax][B*C][2]   out: states of the extended prefixes
  *   status     [U]                 in/out: OR-ed E2E_STATUS_* bits (may be NULL)
+ *   n_run      only utterances 0..n_run-1 are processed (<= 0: all U).  A batch sorted by
+ *              decreasing length keeps its live utterances as a prefix, so finished ones cost nothing;
+ *              U stays the stride of x / history.
  */
 int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int V, const int *enc_len,
                          const float *r_prev, int lanes_prev,
                          const int *prev_lane, const int *last_tok, const int *prefix_len,
                          const int *n_live, const int *cand, int B, int C, int flags,
-                         float *psi, float *r_out, int *status, void *stream);
+                         float *psi, float *r_out, int *status, int n_run, void *stream);
 
 /* (3a) Attention log-softmax statistics + CTC candidate pre-pruning.  Replaces
  * F.log_softmax(cur_prob) and cur_prob.topk(ctc_beam_size) (src/decode.py:122,129-130).
@@ -128,7 +131,8 @@ int e2e_beam_candidates(const float *att_logits, int ld, int U, int B, int V, in
  * Closed (<eos>-terminated) hypotheses are kept per utterance, stably sorted by mean score and
  * truncated to the best fin_cap (>= B, so nothing the final selection could return is lost):
  *   fin_count [U]; fin_step, fin_parent (int32), fin_sum, fin_score (fp32): [U][fin_cap]
- * Utterances with step >= max_len[u] are left untouched.
+ * Utterances with step >= max_len[u] are left untouched; only utterances 0..n_run-1 are visited
+ * (<= 0: all U).
  *   lm_logits may be NULL iff E2E_BEAM_USE_LM is clear; cand/psi iff E2E_BEAM_USE_CTC is clear. */
 int e2e_beam_combine_prune(const float *att_logits, int ld_att, const float *att_stats,
                            const float *lm_logits, int ld_lm,
@@ -141,7 +145,7 @@ int e2e_beam_combine_prune(const float *att_logits, int ld_att, const float *att
                            int *parent_slot,
                            int *hist_tok, int *hist_parent, float *hist_score,
                            int *fin_count, int *fin_step, int *fin_parent, float *fin_sum, float *fin_score,
-                           int fin_cap, int *status, void *stream);
+                           int fin_cap, int *status, int n_run, void *stream);
 
 /* Final N-best selection + back-tracking.  Replaces src/decode.py:180-183 and
  * Hypothesis.outIndex (src/decode.py:279-281): closed hypotheses followed by the last
@@ -154,6 +158,20 @@ int e2e_beam_finalize(int U, int B, const int *max_len,
                       const float *fin_sum, const float *fin_score, int fin_cap,
                       int *out_tok, float *out_score, int *out_len, float *out_avg, int *out_n,
                       int out_cap, void *stream);
+
+/* (next) Fused location-aware attention energies + masked softmax for one
+ * decode step.  Replaces LocationAwareAttention.forward minus the convolution
+ * (src/module.py:1163-1168) and BaseAttention._attend minus the context product
+ * (src/module.py:1109-1113):
+ *   attn[n][t] = softmax_t( (b_e + sum_a w_e[a] * tanh(key[u][t][a] + query[n][a]
+ *                            + tanh(sum_k w_proj[a][k] * loc_feat[n][k][t]))) / temperature ),  t < enc_len[u]
+ * and exactly 0 for t >= enc_len[u]; u = n / B.
+ *   key [U][T][A] (tanh(proj_k(enc)), src/asr.py:343), query [n_hyp][A] (tanh(proj_q(h)), src/asr.py:337),
+ *   loc_feat [n_hyp][K][T] (loc_conv(prev_att), src/module.py:1163), w_proj [A][K], w_energy [A].
+ *   Needs K <= 12 and A % 4 == 0. */
+int e2e_attention_loc_step(const float *key, const float *query, const float *loc_feat, const int *enc_len,
+                           const float *w_proj, const float *w_energy, float b_energy, float temperature,
+                           int n_hyp, int B, int T, int A, int K, float *attn, void *stream);
 
 /* Number of kernel launches issued through this library by the calling process
  * (for bench.py's gpu_launches claim). */

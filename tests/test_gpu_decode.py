@@ -160,3 +160,35 @@ def test_golden_nbest_from_reference(cuda):
         s, _ = _compare(out, ora, "golden case %d" % case)
         same, total = same + s, total + 1
     assert same >= total - 1
+
+
+def test_split_gemm_is_fp32_accurate(cuda):
+    """The recurrent GEMMs run as a 3-way bf16 split on the tensor cores (stepper.SplitLinear).
+    Its error against an fp64 product must not exceed that of cuBLAS' own fp32 GEMM."""
+    from e2e_asr_pytorch_b200.stepper import SplitLinear
+    g = torch.Generator().manual_seed(0)
+    from e2e_asr_pytorch_b200.decode import _Fp32Math
+    with _Fp32Math():
+        for n, k, m in [(256, 2048, 4096), (64, 1240, 1200), (8, 300, 31)]:
+            x = (torch.randn(n, k, generator=g) * 3).to(cuda)
+            w = (torch.randn(m, k, generator=g) / k ** 0.5).to(cuda)
+            b = torch.randn(m, generator=g).to(cuda)
+            want = (x.double() @ w.double().t() + b.double())
+            e_split = (SplitLinear(w, b)(x).double() - want).abs().max().item()
+            e_fp32 = (torch.nn.functional.linear(x, w, b).double() - want).abs().max().item()
+            print("split-gemm %dx%dx%d: max err %.3g (cuBLAS fp32 %.3g)" % (n, k, m, e_split, e_fp32))
+            assert e_split <= 2.0 * e_fp32 + 1e-6
+
+
+def test_decode_batch_is_order_independent(cuda):
+    """decode_batch sorts by length internally; results come back in the caller's order and do not
+    depend on what else is in the batch."""
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth
+    asr, lm, lm_path, lm_cfg = _models()
+    lens = [64, 200, 92, 148, 76]
+    feat, fl = synth.padded_batch(list(range(5)), lens)
+    dec = BeamDecoder(asr, None, 4, 0.01, 0.2, lm_path=lm_path, lm_config=lm_cfg, lm_weight=0.5, ctc_weight=0.5).to(cuda)
+    both = dec.decode_batch(feat.to(cuda), fl.to(cuda))
+    for k, n in enumerate(lens):
+        alone = dec(feat[k:k + 1, :n].to(cuda), fl[k:k + 1].to(cuda))
+        assert [h.outIndex for h in alone] == [h.outIndex for h in both[k]], k
