@@ -338,8 +338,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-utts", type=int, default=N_UTTS, help="utterances per GPU (profiling runs only; the metric is quoted on 2620)")
-    ap.add_argument("--max-utts", type=int, default=1024)
-    ap.add_argument("--max-padded-frames", type=int, default=700000)
+    ap.add_argument("--max-utts", type=int, default=4096)
+    ap.add_argument("--max-padded-frames", type=int, default=0)
     ap.add_argument("--fast-math", type=int, default=0)
     ap.add_argument("--write-dead-rows", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

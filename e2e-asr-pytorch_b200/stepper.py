@@ -156,16 +156,33 @@ class BatchedStepper:
                 self._b_energy = float(lay.gen_energy.bias.detach().reshape(-1)[0])
 
     # -- once per batch ---------------------------------------------------------------------
-    def encode(self, feats, lens):
-        """feats [U,Lmax,D] zero padded, lens [U] -> enc [U,Tmax,E], enc_len [U] (long, same device)."""
+    def encode(self, feats, lens, chunk=128):
+        """feats [U,Lmax,D] zero padded, lens [U] -> enc [U,Tmax,E], enc_len [U] (long, same device).
+        The batch is encoded ``chunk`` utterances at a time, each chunk cropped to its own longest
+        utterance: with the batch sorted by length this removes most of the padding work."""
         enc_mod = self.asr.encoder
-        if feats.shape[0] == 1:
+        n_utts = feats.shape[0]
+        if n_utts == 1:
             enc, enc_len = enc_mod(feats, lens)
         elif hasattr(enc_mod, "forward_ragged"):
-            enc, enc_len = enc_mod.forward_ragged(feats, lens)
+            lens_host = lens.cpu()
+            outs, ls = [], []
+            for lo in range(0, n_utts, chunk):
+                hi = min(n_utts, lo + chunk)
+                l_max = int(lens_host[lo:hi].max())
+                e, l = enc_mod.forward_ragged(feats[lo:hi, :l_max], lens[lo:hi])
+                outs.append(e)
+                ls.append(l.reshape(-1))
+            t_all = max(e.shape[1] for e in outs)
+            enc = feats.new_zeros((n_utts, t_all, outs[0].shape[2]))
+            lo = 0
+            for e in outs:
+                enc[lo:lo + e.shape[0], :e.shape[1]] = e
+                lo += e.shape[0]
+            enc_len = torch.cat(ls)
         else:   # opaque encoder (e.g. the reference's own module): one exact batch-1 call per utterance
             outs, ls = [], []
-            for i in range(feats.shape[0]):
+            for i in range(n_utts):
                 n = int(lens[i])
                 e, l = enc_mod(feats[i:i + 1, :n], lens[i:i + 1])
                 outs.append(e[0])

@@ -169,7 +169,7 @@ def test_split_gemm_is_fp32_accurate(cuda):
     g = torch.Generator().manual_seed(0)
     from e2e_asr_pytorch_b200.decode import _Fp32Math
     with _Fp32Math():
-        for n, k, m in [(256, 2048, 4096), (64, 1240, 1200), (8, 300, 31)]:
+        for n, k, m in [(2048, 2048, 4096), (1024, 1240, 1200), (1536, 1024, 4096), (8, 300, 31)]:
             x = (torch.randn(n, k, generator=g) * 3).to(cuda)
             w = (torch.randn(m, k, generator=g) / k ** 0.5).to(cuda)
             b = torch.randn(m, generator=g).to(cuda)

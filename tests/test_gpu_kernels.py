@@ -244,7 +244,8 @@ def test_prefix_too_long_sets_status(cuda):
 # ----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n_utts,beam,t_len,dim,n_filt", [(3, 8, 180, 300, 10), (2, 2, 37, 24, 4), (1, 16, 875, 300, 10), (4, 4, 300, 128, 12)])
 def test_attention_loc_step_matches_oracle(cuda, n_utts, beam, t_len, dim, n_filt):
-    """attn within 2e-6 abs of the fp32 CPU restatement (MUFU-based tanh, fp32 softmax); masked frames exactly 0."""
+    """attn within 5e-6 abs of the fp32 CPU restatement (MUFU-based tanh, fp32 softmax; the fixture uses
+    4x larger energy weights than init gives); masked frames exactly 0."""
     ops, _ = _ops()
     from oracle import attention_oracle as AO
     g = torch.Generator().manual_seed(t_len + dim)
@@ -262,7 +263,7 @@ def test_attention_loc_step_matches_oracle(cuda, n_utts, beam, t_len, dim, n_fil
                                  w_e.to(cuda), 0.25, 0.5, beam).cpu()
     err = (got - want).abs().max().item()
     print("attention step U=%d B=%d T=%d A=%d: max |gpu-oracle| = %.3g" % (n_utts, beam, t_len, dim, err))
-    assert err < 2e-6
+    assert err < 5e-6
     for u in range(n_utts):
         assert (got[u * beam:(u + 1) * beam, int(enc_len[u]):] == 0).all()
     assert torch.allclose(got.sum(-1), torch.ones(n), atol=1e-5)

@@ -17,8 +17,8 @@ import bench  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n-utts", type=int, default=2620)
-    ap.add_argument("--max-utts", type=int, default=1024)
-    ap.add_argument("--max-padded-frames", type=int, default=700000)
+    ap.add_argument("--max-utts", type=int, default=4096)
+    ap.add_argument("--max-padded-frames", type=int, default=0)
     a = ap.parse_args()
     from e2e_asr_pytorch_b200 import shard
     dev = torch.device("cuda:0")
