@@ -25,8 +25,9 @@ Two things keep the library GEMMs off the critical path without leaving fp32:
   the result is as accurate as cuBLAS' fp32 SIMT GEMM (tests/test_gpu_decode.py
   checks it against fp64) at less than half its time;
 * ``fused_attention``: the location-aware energies + masked softmax run in one
-  hand-written kernel (csrc/attention_step.cu) instead of ~8 passes over
-  [U*B, T, 300] temporaries.
+  hand-written kernel (csrc/attention_full.cu: location convolution, energies, masked
+  softmax and the context product) instead of a cuDNN convolution, ~8 passes over
+  [U*B, T, 300] temporaries and a batched GEMM, and never touches padded frames.
 """
 import numpy as np
 import torch
@@ -151,6 +152,7 @@ class BatchedStepper:
             lay = att.att_layer
             if lay.loc_proj.weight.shape[1] <= 12 and lay.loc_proj.weight.shape[0] % 4 == 0:
                 self.fused_attention = True
+                self._w_conv = lay.loc_conv.weight.detach()[:, 0, :].contiguous()           # [K, 2P+1]
                 self._w_proj = lay.loc_proj.weight.detach().contiguous()
                 self._w_energy = lay.gen_energy.weight.detach().reshape(-1).contiguous()
                 self._b_energy = float(lay.gen_energy.bias.detach().reshape(-1)[0])
@@ -224,9 +226,10 @@ class BatchedStepper:
         query = torch.tanh(att.proj_q(torch.cat([h[:n] for h in self.dec_state[0]], dim=1)))   # asr.py:337 / :251-254
         if self.mode == "loc" and self.fused_attention:
             from . import ops
-            feat = att.att_layer.loc_conv(self.prev_att[:n, None, :]).contiguous()     # [n,K,T]  module.py:1163 (cuDNN)
-            attn = ops.attention_loc_step(self.key, query.contiguous(), feat, self._enc_len32, self._w_proj,
-                                          self._w_energy, self._b_energy, self.temperature, b).view(k, b, t)
+            # conv + energies + masked softmax + context in one kernel (csrc/attention_full.cu)
+            attn, context = ops.attention_loc_full(self.key, self.value, query.contiguous(), self.prev_att, self._enc_len32,
+                                                   self._w_conv, self._w_proj, self._w_energy, self._b_energy,
+                                                   self.temperature, b, n_run=k)
         else:
             if self.mode == "loc":
                 lay = att.att_layer
@@ -238,7 +241,7 @@ class BatchedStepper:
                 energy = torch.bmm(query.view(k, b, -1), self.key[:k].transpose(1, 2))  # module.py:1126
             score = (energy / self.temperature).masked_fill(self.pad[:k, None, :], -np.inf)
             attn = torch.softmax(score, dim=-1)                                        # [k,B,T]
-        context = torch.bmm(attn, self.value[:k]).view(n, -1)                      # module.py:1114
+            context = torch.bmm(attn, self.value[:k]).view(n, -1)                      # module.py:1114
         self.mark("step_attention")
         dec_in = torch.cat([asr.pre_embed(prev_tok), context], dim=-1)             # decode.py:114-115
         top, self._new_dec = self.dec.step(dec_in, self.dec_state, n)

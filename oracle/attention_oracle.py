@@ -22,3 +22,17 @@ def loc_attention_step(key, query, loc_feat, enc_len, w_proj, w_energy, b_energy
     pad = torch.arange(t)[None, :] >= torch.as_tensor(enc_len).long()[u_of][:, None]
     score = (energy / temperature).masked_fill(pad, -np.inf)                      # module.py:1110-1111
     return torch.softmax(score, dim=-1)                                           # module.py:1112
+
+
+def loc_attention_full(key, value, query, prev_att, enc_len, w_conv, w_proj, w_energy, b_energy, temperature, beam):
+    """The whole step, module.py:1152-1173 + :1109-1117: conv (Conv1d 1->K, zero padded, no bias) ->
+    :func:`loc_attention_step` -> context.  value [U,T,E], prev_att [N,T], w_conv [K,W] -> (attn [N,T], ctx [N,E])."""
+    prev_att = torch.as_tensor(prev_att, dtype=torch.float32)
+    w_conv = torch.as_tensor(w_conv, dtype=torch.float32)
+    value = torch.as_tensor(value, dtype=torch.float32)
+    pad = w_conv.shape[1] // 2
+    feat = torch.nn.functional.conv1d(prev_att[:, None, :], w_conv[:, None, :], padding=pad)     # module.py:1163
+    attn = loc_attention_step(key, query, feat, enc_len, w_proj, w_energy, b_energy, temperature, beam)
+    u_of = torch.arange(attn.shape[0]) // beam
+    ctx = torch.bmm(attn[:, None, :], value[u_of]).squeeze(1)                                      # module.py:1114
+    return attn, ctx

@@ -267,3 +267,47 @@ def test_attention_loc_step_matches_oracle(cuda, n_utts, beam, t_len, dim, n_fil
     for u in range(n_utts):
         assert (got[u * beam:(u + 1) * beam, int(enc_len[u]):] == 0).all()
     assert torch.allclose(got.sum(-1), torch.ones(n), atol=1e-5)
+
+
+@pytest.mark.parametrize("n_utts,beam,t_len,dim,n_filt,half,e_dim", [(3, 8, 180, 300, 10, 100, 640), (2, 2, 37, 24, 4, 10, 40),
+                                                                     (1, 16, 875, 300, 10, 100, 640), (4, 3, 300, 128, 12, 25, 96),
+                                                                     (2, 1, 50, 32, 7, 3, 17)])
+def test_attention_loc_full_matches_oracle(cuda, n_utts, beam, t_len, dim, n_filt, half, e_dim):
+    """Whole attention step (conv + energies + softmax + context): attn within 5e-6 abs, context within 2e-5 abs
+    of the fp32 CPU restatement; identical results for every hypotheses-per-CTA grouping; only the first n_run
+    utterances are written."""
+    ops, _ = _ops()
+    from oracle import attention_oracle as AO
+    g = torch.Generator().manual_seed(t_len + dim)
+    n = n_utts * beam
+    key = torch.tanh(torch.randn(n_utts, t_len, dim, generator=g))
+    value = torch.randn(n_utts, t_len, e_dim, generator=g)
+    query = torch.tanh(torch.randn(n, dim, generator=g))
+    enc_len = torch.tensor([max(1, t_len - 7 * i) for i in range(n_utts)], dtype=torch.int32)
+    prev = torch.softmax(torch.randn(n, t_len, generator=g) * 2, -1)
+    for i in range(n):                                  # previous alignments are zero beyond the utterance
+        prev[i, int(enc_len[i // beam]):] = 0
+    conv_w = torch.randn(n_filt, 2 * half + 1, generator=g) * 0.3
+    w_proj = torch.randn(dim, n_filt, generator=g) / n_filt ** 0.5
+    w_e = torch.randn(dim, generator=g) / dim ** 0.5 * 4
+    want_a, want_c = AO.loc_attention_full(key, value, query, prev, enc_len, conv_w, w_proj, w_e, 0.25, 0.5, beam)
+    dev = lambda t: t.to(cuda)
+    outs = []
+    for nb in (0, 1, 2, 4):
+        got_a, got_c = ops.attention_loc_full(dev(key), dev(value), dev(query), dev(prev), dev(enc_len), dev(conv_w), dev(w_proj),
+                                              dev(w_e), 0.25, 0.5, beam, hyps_per_cta=nb)
+        outs.append((got_a.cpu(), got_c.cpu()))
+    got_a, got_c = outs[0]
+    err_a, err_c = (got_a - want_a).abs().max().item(), (got_c - want_c).abs().max().item()
+    print("attention full U=%d B=%d T=%d A=%d: max |gpu-oracle| attn %.3g ctx %.3g" % (n_utts, beam, t_len, dim, err_a, err_c))
+    assert err_a < 5e-6 and err_c < 2e-5
+    for a, c in outs[1:]:
+        assert torch.equal(a, got_a) and torch.equal(c, got_c)
+    for u in range(n_utts):
+        assert (got_a[u * beam:(u + 1) * beam, int(enc_len[u]):] == 0).all()
+    if n_utts > 1:                                      # n_run: rows of later utterances stay untouched
+        attn = torch.full((n, t_len), -7.0, device=cuda)
+        ctx = torch.full((n, e_dim), -7.0, device=cuda)
+        ops.attention_loc_full(dev(key), dev(value), dev(query), dev(prev), dev(enc_len), dev(conv_w), dev(w_proj), dev(w_e),
+                               0.25, 0.5, beam, n_run=1, attn=attn, ctx=ctx)
+        assert torch.equal(attn[:beam].cpu(), got_a[:beam]) and (attn[beam:] == -7.0).all() and (ctx[beam:] == -7.0).all()
