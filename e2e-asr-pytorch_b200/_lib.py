@@ -19,6 +19,7 @@ PREFIX_FULL = 1
 PREFIX_SKIP_DEAD_ROWS = 2
 PREFIX_FAST_MATH = 4
 PREFIX_LIBM_MATH = 8
+PREFIX_ROW_COPIES = 16
 BEAM_USE_CTC = 1
 BEAM_USE_LM = 2
 

@@ -33,6 +33,10 @@ __device__ const float4 kSoftplusLut[kLutNodes] = {
 #include "softplus_lut.inc"
 };
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
 __device__ __forceinline__ float ex2_approx(float x)
 {
     float y;
@@ -52,33 +56,45 @@ __device__ __forceinline__ void softplus_lut_to_smem(float4 *dst, int tid, int n
     for (int i = tid; i < kLutNodes * kLutCopies; i += nt) dst[i] = kSoftplusLut[i / kLutCopies];
 }
 
-// nd = -|a-b| <= 0.  lut points at this lane's replica (base + (lane & 7)).
-__device__ __forceinline__ float softplus_lut(float nd, const float4 *lut)
+// ad = |a-b| >= 0; returns softplus(-ad).  lut points at this lane's replica (base + (lane & 7)).
+// tm = -16*min(ad,4) + (1.5*2^23 + 64) has the node index in its low mantissa bits:
+// bits(tm) = 0x4B400000 + idx, idx in [0,64].  The table entry sits idx*128 bytes after the replica
+// base, so its shared-memory address is (bits(tm) << 7) + (base - (0x4B400000 << 7)) in 32-bit
+// wrap-around arithmetic: one LEA instead of mask + shift + add.
+__device__ __forceinline__ float softplus_lut(float ad, uint32_t lut_adj)
 {
     const float kMagic = 12582912.0f + 64.0f;           // 1.5*2^23 + index bias
-    const float t = fmaxf(nd * 16.0f, -64.0f);           // node units, clamped to the table
-    const float tm = __fadd_rn(t, kMagic);               // low mantissa bits = round(t) + 64
-    const float f = __fsub_rn(t, __fsub_rn(tm, kMagic)); // exact fraction in [-0.5, 0.5]
-    const float4 c = lut[(__float_as_int(tm) & 0x7f) * kLutCopies];
+    const float tc = fminf(ad, 4.0f);                    // clamped to the table, [-4, 0] in node units of 1/16
+    const float tm = fmaf(tc, -16.0f, kMagic);           // low mantissa bits = round(-16 tc) + 64
+    const float f = fmaf(tc, -16.0f, __fsub_rn(kMagic, tm)); // exact fraction in [-0.5, 0.5]
+    float4 c;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+        : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w)
+        : "r"((static_cast<uint32_t>(__float_as_int(tm)) << 7) + lut_adj));
     const float g = fmaf(f, fmaf(f, fmaf(f, c.w, c.z), c.y), c.x);
     // d < -4: e = exp(d) <= 0.0184, log1p(e) = e(1 - e/2 + e^2/3 - e^3/4) to 4e-10
-    const float e = ex2_approx(nd * 1.4426950408889634f);
+    const float e = ex2_approx(ad * -1.4426950408889634f);
     const float q = fmaf(e, fmaf(e, fmaf(e, -0.25f, 0.333333343f), -0.5f), 1.0f);
-    return nd < -4.0f ? e * q : g;
+    return ad > 4.0f ? e * q : g;
+}
+// The address operand of softplus_lut for a thread whose replica starts at `lut`.
+__device__ __forceinline__ uint32_t softplus_lut_adj(const float4 *lut)
+{
+    return smem_u32(lut) - (0x4B400000u << 7);
 }
 
 template <int kMath>
-__device__ __forceinline__ float logaddexp(float a, float b, const float4 *lut)
+__device__ __forceinline__ float logaddexp(float a, float b, uint32_t lut)
 {
     const float m = fmaxf(a, b);
-    const float nd = -fabsf(a - b);
+    const float ad = fabsf(a - b);
     float l;
     if (kMath == kMathLut) {
-        l = softplus_lut(nd, lut);
+        l = softplus_lut(ad, lut);
     } else if (kMath == kMathMufu) {
-        l = lg2_approx(1.0f + ex2_approx(nd * 1.4426950408889634f)) * E2E_LN2F;
+        l = lg2_approx(1.0f + ex2_approx(ad * -1.4426950408889634f)) * E2E_LN2F;
     } else {
-        l = (nd == 0.0f) ? E2E_LN2F : log1pf(expf(nd));
+        l = (ad == 0.0f) ? E2E_LN2F : log1pf(expf(-ad));
     }
     return __fadd_rn(m, l);
 }
@@ -108,10 +124,6 @@ __device__ __forceinline__ void warp_argmax(float &v, int &i)
 }
 
 // ---- mbarrier + bulk async copy (TMA engine, SASS: UBLKCP / SYNCS) --------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -6,31 +6,39 @@
 // t = start..T-1 sequentially in fp32 (the reference's order).  Per frame it needs
 //     r0' = logaddexp(r0, phi) + x_c      r1' = logaddexp(r1, r0) + x_blank       (the recurrence)
 //     psi = logaddexp(psi, phi + x_c)                                              (a running reduction)
-// psi never feeds back into r, so every lane is served by TWO threads of the same CTA: a
-// "state" thread carries (r0, r1) and streams them out as one coalesced float2 per frame, a
-// "psi" thread carries psi.  That doubles the independent dependency chains in flight per
-// utterance, which is what the sequential-in-T recursion is starved of.
-// A CTA covers up to 128 consecutive lanes of ONE utterance (2x that many threads), so its
-// threads share the utterance's posterior rows x[t][u][:] and the few parent states.
-// Frames are processed in tiles of kTile:
+// i.e. three log-add-exp that only meet through r0.  The kernel is bound by instruction issue,
+// not by HBM, so the layout minimises instructions per
+// candidate-frame: ONE thread per lane carries all three chains (the three log-add-exp are
+// independent inside a frame, so the thread itself has the instruction-level parallelism that
+// hides their latency; the phi and x_c loads are shared by two of them), every per-frame address
+// is a constant offset from a pointer that is bumped once per 4 frames, and the state leaves as
+// one coalesced float2 per lane per frame.
+// A CTA covers up to 128 consecutive lanes of ONE utterance, so its threads share the
+// utterance's posterior rows x[t][u][:] and the few parent states.  Frames are processed in
+// tiles of kTile:
 //   * "rows" variant (Vp <= kMaxRowFloats): the tile's posterior rows are brought into shared
-//     memory by the TMA engine (cp.async.bulk, one 16B-aligned row per copy, completion on an
-//     mbarrier), double buffered, so the gather x[t][cand] becomes a conflict-free LDS;
-//   * "gather" variant (large vocabularies): each state thread fetches its own column
+//     memory by the TMA engine, double buffered, completion on an mbarrier, so the gather
+//     x[t][cand] becomes a conflict-free LDS.  The tile is a [kTile frames] x [1 utterance] x [Vp]
+//     box of the frame-major [T][U][Vp] tensor: ONE cp.async.bulk.tensor (UTMALDG) through a
+//     tensor map built by the host wrapper; E2E_PREFIX_ROW_COPIES selects the older form, one
+//     cp.async.bulk (UBLKCP) per 16B-aligned row, which costs the issuing warp a 32-trip loop;
+//   * "gather" variant (large vocabularies): each thread fetches its own column
 //     x[t][u][cand] for the whole tile with independent loads and parks it in shared memory.
 //   The parents' states are turned into phi tiles in shared memory once per hypothesis
 //     phi[h][t] = ( logaddexp(r_prev[t][0], r_prev[t][1]),  r_prev[t][1] )
-//   and are software pipelined: the global loads for tile k+1 are issued before tile k is
-//   computed, so one __syncthreads per tile is all the synchronisation there is.
+//   and are software pipelined without holding registers: the raw states of tile k+1 are
+//   copied into a staging buffer with cp.async (LDGSTS) before tile k is computed and turned into
+//   phi afterwards, so one __syncthreads per tile is all the synchronisation there is.
 #include "common.cuh"
+#include <string.h>
+#include <cuda.h>      // CUtensorMap (types only; the encoder is fetched from the driver at run time)
 
 namespace e2e {
 
 constexpr int kTile = 32;            // frames per shared-memory tile
-constexpr int kPhiPitch = kTile + 1; // float2 pitch of a phi row (odd: no bank conflicts across hypotheses)
+constexpr int kPhiPitch = 2 * kTile + 2; // floats per phi row: 32 x (sum, blank) + pad (bank spread across hypotheses)
 constexpr int kMaxRowFloats = 256;   // rows variant up to 1 KB per posterior row
-constexpr int kMaxLanes = 128;       // lanes per CTA (threads = 2 x lanes)
-constexpr int kPrefetch = 2;         // phi entries per thread held in registers across a tile
+constexpr int kMaxLanes = 128;       // lanes (= threads) per CTA
 constexpr int kLutBytes = kLutNodes * kLutCopies * 16;
 
 struct PrefixParams {
@@ -41,52 +49,75 @@ struct PrefixParams {
     int B, C, flags;
     float *psi; float2 *r_out; int *status;
     int chunks_per_utt;   // CTAs per utterance
-    int lanes_per_cta;    // multiple of 32; blockDim.x = 2 * lanes_per_cta
+    int lanes_per_cta;    // multiple of 32 = blockDim.x
     int hyps_per_cta;     // rows of the phi tile
 };
 
 __host__ __device__ inline size_t prefix_xs_bytes(bool gather, int lanes, int Vp)
 {
-    size_t f = gather ? (size_t)kTile * lanes + kTile : (size_t)2 * kTile * Vp;
+    // rows: two tiles of kTile posterior rows.  gather: two tiles of per-lane columns + the blank column.
+    size_t f = gather ? (size_t)2 * (kTile * lanes + kTile) : (size_t)2 * kTile * Vp;
     return ((f + 3) & ~(size_t)3) * 4;
 }
-__host__ __device__ inline size_t prefix_phis_bytes(int H) { return (size_t)2 * H * kPhiPitch * 8; }
+__host__ __device__ inline size_t prefix_phis_bytes(int H) { return (size_t)2 * H * kPhiPitch * 4; }
+__host__ __device__ inline size_t prefix_stage_bytes(int H) { return (size_t)H * kTile * 8; }   // raw parent states of one tile
 
-template <bool kGather, int kMath>
-__global__ void __launch_bounds__(2 * kMaxLanes, 5)
-prefix_score_kernel(const PrefixParams p)
+// kVp / kLU: compile-time copies of Vp and B*C for the shapes the beam search runs all day
+// (0 = take them from the parameters): per-frame offsets then become instruction immediates.
+// 3-D tiled TMA load: box (Vp, 1, kTile) at coordinates (0, u, t0) of the [Tmax][U][Vp] posterior tensor.
+__device__ __forceinline__ void tma_load_tile(void *dst_smem, const CUtensorMap *map, int u, int t0, uint64_t *bar)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(0), "r"(u), "r"(t0), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void *dst_smem, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+template <bool kGather, int kMath, int kVp, int kLU, bool kTmap>
+__global__ void __launch_bounds__(kMaxLanes, 8)
+prefix_score_kernel(const PrefixParams p, const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int nl = p.lanes_per_cta;
-    const bool psi_role = tid >= nl;              // warp uniform (nl is a multiple of 32)
-    const int lt = psi_role ? tid - nl : tid;     // lane index within the CTA
+    const int nl = nt;
+    const int lt = tid;                           // lane index within the CTA
     const int u = blockIdx.x / p.chunks_per_utt;
     const int chunk = blockIdx.x % p.chunks_per_utt;
     const int T = p.enc_len ? p.enc_len[u] : p.Tmax;
     const int live = p.n_live ? p.n_live[u] : p.B;
-    const int C = p.C, LU = p.B * p.C;
+    const int C = p.C;
+    const int LU = kLU ? kLU : p.B * p.C;
+    const int Vp = kVp ? kVp : p.Vp;
     const int lane0 = chunk * nl;                 // first lane (within the utterance) of this CTA
     if (T <= 0 || lane0 >= live * C) return;      // nothing to do for this CTA (uniform exit)
     const bool full = (p.flags & E2E_PREFIX_FULL) != 0;
     const bool fill_dead = (p.flags & E2E_PREFIX_SKIP_DEAD_ROWS) == 0;
 
-    // ---- shared memory: LUT replicas | x tiles | phi tiles (x2) | s_plane[H] | s_red[2] | mbarriers[2]
+    // ---- shared memory: LUT replicas | x tiles | phi tiles (x2) | raw parent states | s_plane[H] | s_red[2] | mbarriers[2]
     const int H = p.hyps_per_cta;
     const size_t xs_off = kLutBytes;
-    const size_t phis_off = xs_off + prefix_xs_bytes(kGather, nl, p.Vp);
-    const size_t misc_off = phis_off + prefix_phis_bytes(H);
+    const size_t phis_off = xs_off + prefix_xs_bytes(kGather, nl, Vp);
+    const size_t stage_off = phis_off + prefix_phis_bytes(H);
+    const size_t misc_off = stage_off + prefix_stage_bytes(H);
     const size_t bars_off = (misc_off + (size_t)(H + 2) * 4 + 7) & ~(size_t)7;
     float4 *lut_base = reinterpret_cast<float4 *>(smem_raw);
     float *xs = reinterpret_cast<float *>(smem_raw + xs_off);
-    float2 *phis = reinterpret_cast<float2 *>(smem_raw + phis_off);
+    float *phis = reinterpret_cast<float *>(smem_raw + phis_off);
+    float2 *stage_buf = reinterpret_cast<float2 *>(smem_raw + stage_off);
     int *s_plane = reinterpret_cast<int *>(smem_raw + misc_off);
     int *s_red = s_plane + H;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + bars_off);
-    const float4 *lut = lut_base + (tid & (kLutCopies - 1));      // this thread's replica
-    float *xb_g = xs + (size_t)kTile * nl;                        // gather variant only
+    const uint32_t lut = softplus_lut_adj(lut_base + (tid & (kLutCopies - 1)));   // this thread's replica
+    const int g_tile = kTile * nl + kTile;                        // gather variant: floats per x tile
 
-    // ---- per-lane setup (identical in both roles) ---------------------------------------------
+    // ---- per-lane setup -----------------------------------------------------------------------
     const int lane_u = lane0 + lt;                // lane within the utterance
     const bool active = lane_u < live * C;
     const int h = active ? lane_u / C : 0;        // beam slot
@@ -101,7 +132,7 @@ prefix_score_kernel(const PrefixParams p)
     }
     const int start = plen > 1 ? plen : 1;
     const bool too_long = active && (start - 1 >= T);
-    if (too_long && !psi_role && p.status) atomicOr(p.status + u, E2E_STATUS_PREFIX_TOO_LONG);
+    if (too_long && p.status) atomicOr(p.status + u, E2E_STATUS_PREFIX_TOO_LONG);
     const bool run = active && !too_long;
     const bool special = full ? (tok == (plen > 0 ? ltok : 0)) : (plen > 0 && tok == ltok);
 
@@ -117,11 +148,11 @@ prefix_score_kernel(const PrefixParams p)
         mbar_fence_init();
     }
     __syncthreads();
-    if (run && !psi_role) atomicMin(&s_red[0], start);
+    if (run) atomicMin(&s_red[0], start);
     __syncthreads();
     const int cta_start = s_red[0];               // 0x7fffffff if no lane runs
-    const long long xrow0 = (long long)u * p.Vp;  // x[t][u][:] = x + t*U*Vp + xrow0
-    const long long xstride = (long long)p.U * p.Vp;
+    const long long xrow0 = (long long)u * Vp;    // x[t][u][:] = x + t*U*Vp + xrow0
+    const long long xstride = (long long)p.U * Vp;
     float2 *__restrict__ rout = p.r_out + ((long long)u * p.Tmax) * LU + lane_u;
     const float2 *__restrict__ rprev_u = p.r_prev + ((long long)u * p.Tmax) * p.lanes_prev;
     const float2 dead = make_float2(E2E_CTC_LOGZERO, E2E_CTC_LOGZERO);
@@ -134,152 +165,184 @@ prefix_score_kernel(const PrefixParams p)
         const int first_tile = cta_start / kTile;
         const int n_tiles = (T + kTile - 1) / kTile;
         // rows below the first computed tile are log-zero by construction
-        if (run && !psi_role && fill_dead)
+        if (run && fill_dead)
             for (int t = 0; t < first_tile * kTile && t < T; ++t) rout[(long long)t * LU] = dead;
 
-        auto issue_rows = [&](int k) {   // warp 0: one bulk copy per posterior row of tile k
+        auto issue_rows = [&](int k) {   // warp 0 brings posterior tile k into its ring stage
             const int t0 = k * kTile;
-            const int rows = min(kTile, T - t0);
             uint64_t *bar = &bars[k & 1];
-            float *dst = xs + (size_t)(k & 1) * kTile * p.Vp;
-            if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)rows * p.Vp * 4u);
-            __syncwarp();
-            if (tid < rows)
-                bulk_g2s(dst + (size_t)tid * p.Vp, p.x + (long long)(t0 + tid) * xstride + xrow0, (uint32_t)p.Vp * 4u, bar);
+            float *dst = xs + (size_t)(k & 1) * kTile * Vp;
+            if (kTmap) {
+                // one box copy; frames beyond Tmax are zero filled by the TMA unit and still count as bytes
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(bar, (uint32_t)kTile * Vp * 4u);
+                    tma_load_tile(dst, &tmap, u, t0, bar);
+                }
+            } else {
+                const int rows = min(kTile, T - t0);
+                if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)rows * Vp * 4u);
+                __syncwarp();
+                if (tid < rows)
+                    bulk_g2s(dst + (size_t)tid * Vp, p.x + (long long)(t0 + tid) * xstride + xrow0, (uint32_t)Vp * 4u, bar);
+            }
         };
-        // phi tile k, entry (hl, tt) describes r_prev at frame k*kTile + tt - 1
+        // phi tile k, entry (hl, tt) describes r_prev at frame k*kTile + tt - 1.  Entry i of a tile is
+        // fetched (phi_fetch) and converted (phi_convert) by the same thread, so cp.async.wait_all is
+        // all the ordering the staging buffer needs.
         const int n_phi = H * kTile;
-        auto phi_fetch = [&](int k, int i) -> float2 {
-            const int hl = i / kTile, tt = i - hl * kTile;
-            const int ts = k * kTile + tt - 1;
-            const int pl = s_plane[hl];
-            return (pl >= 0 && ts >= 0 && ts < T) ? __ldg(rprev_u + (long long)ts * p.lanes_prev + pl) : dead;
-        };
-        auto phi_put = [&](int k, int i, float2 a) {
-            const int hl = i / kTile, tt = i - hl * kTile;
-            float2 ph;
-            ph.x = logaddexp<kMath>(a.x, a.y, lut);
-            ph.y = full ? logaddexp<kMath>(E2E_CTC_LOGZERO, a.y, lut) : a.y;
-            phis[(size_t)(k & 1) * H * kPhiPitch + hl * kPhiPitch + tt] = ph;
-        };
-        auto phi_load = [&](int k, float2 (&reg)[kPrefetch]) {
-#pragma unroll
-            for (int q = 0; q < kPrefetch; ++q) {
-                const int i = tid + q * nt;
-                if (i < n_phi) reg[q] = phi_fetch(k, i);
+        auto phi_fetch = [&](int k) {
+            for (int i = tid; i < n_phi; i += nt) {
+                const int hl = i / kTile, tt = i - hl * kTile;
+                const int ts = k * kTile + tt - 1;
+                const int pl = s_plane[hl];
+                if (pl >= 0 && ts >= 0 && ts < T) cp_async_8(stage_buf + i, rprev_u + (long long)ts * p.lanes_prev + pl);
+                else stage_buf[i] = dead;
             }
         };
-        auto phi_store = [&](int k, const float2 (&reg)[kPrefetch]) {
-#pragma unroll
-            for (int q = 0; q < kPrefetch; ++q) {
-                const int i = tid + q * nt;
-                if (i < n_phi) phi_put(k, i, reg[q]);
+        auto phi_convert = [&](int k) {
+            cp_async_wait_all();
+            for (int i = tid; i < n_phi; i += nt) {
+                const int hl = i / kTile, tt = i - hl * kTile;
+                const float2 a = stage_buf[i];
+                float2 ph;
+                ph.x = logaddexp<kMath>(a.x, a.y, lut);
+                ph.y = full ? logaddexp<kMath>(E2E_CTC_LOGZERO, a.y, lut) : a.y;
+                *reinterpret_cast<float2 *>(phis + (size_t)(k & 1) * H * kPhiPitch + hl * kPhiPitch + 2 * tt) = ph;
             }
-            for (int i = tid + kPrefetch * nt; i < n_phi; i += nt) phi_put(k, i, phi_fetch(k, i));   // unusual shapes only
         };
 
-        float2 pf[kPrefetch];
-#pragma unroll
-        for (int q = 0; q < kPrefetch; ++q) pf[q] = dead;
         if (first_tile < n_tiles) {
             if (!kGather && tid < 32) {
                 issue_rows(first_tile);
                 if (first_tile + 1 < n_tiles) issue_rows(first_tile + 1);
             }
-            phi_load(first_tile, pf);
-            phi_store(first_tile, pf);
+            phi_fetch(first_tile);
+            phi_convert(first_tile);
         }
 
-        uint32_t parity[2] = {0u, 0u};
+        // this thread's column inside a phi row (sum or blank-only variant)
+        const int phi_col = (h - h_lo) * kPhiPitch + (special ? 1 : 0);
+        uint32_t parity = 0u;                                  // bit s = phase of mbarrier s
         for (int k = first_tile; k < n_tiles; ++k) {
             const int t0 = k * kTile;
             const int rows = min(kTile, T - t0);
-            if (k + 1 < n_tiles) phi_load(k + 1, pf);          // in flight while tile k is computed
-            const float *xt;   // tile base: xt[tt*pitch + col]
-            int pitch, col;
+            if (k + 1 < n_tiles) phi_fetch(k + 1);             // in flight while tile k is computed
+            const float *xcp, *xbp;   // this thread's candidate column / the blank column of tile row 0
             if (kGather) {
-                __syncthreads();                               // everyone is done with the previous tile's columns
-                if (active && !psi_role) {
+                float *xg = xs + (size_t)(k & 1) * g_tile;     // double buffered: no barrier before the fill
+                if (active) {
 #pragma unroll 8
                     for (int tt = 0; tt < rows; ++tt)
-                        xs[tt * nl + lt] = __ldg(p.x + (long long)(t0 + tt) * xstride + xrow0 + tok);
+                        xg[tt * nl + lt] = __ldg(p.x + (long long)(t0 + tt) * xstride + xrow0 + tok);
                 }
-                if (tid < rows) xb_g[tid] = __ldg(p.x + (long long)(t0 + tid) * xstride + xrow0 + E2E_CTC_BLANK);
-                xt = xs; pitch = nl; col = lt;
+                if (tid < rows) xg[kTile * nl + tid] = __ldg(p.x + (long long)(t0 + tid) * xstride + xrow0 + E2E_CTC_BLANK);
+                xcp = xg + lt; xbp = xg + kTile * nl;
             } else {
-                mbar_wait(&bars[k & 1], parity[k & 1]);
-                parity[k & 1] ^= 1u;
-                xt = xs + (size_t)(k & 1) * kTile * p.Vp; pitch = p.Vp; col = tok;
+                mbar_wait(&bars[k & 1], (parity >> (k & 1)) & 1u);
+                parity ^= 1u << (k & 1);
+                const float *xt = xs + (size_t)(k & 1) * kTile * Vp;
+                xcp = xt + tok; xbp = xt + E2E_CTC_BLANK;
             }
+            const int xc_step = kGather ? nl : Vp, xb_step = kGather ? 1 : Vp;
             __syncthreads();    // phi tile k and x tile k visible; all threads have left tile k-1
             if (!kGather && tid < 32 && k > first_tile && k + 1 < n_tiles) issue_rows(k + 1);   // reuses tile k-1's buffer
             if (run) {
-                const float2 *ph_row = phis + (size_t)(k & 1) * H * kPhiPitch + (size_t)(h - h_lo) * kPhiPitch;
                 int tt = 0;
                 const int tt_first = start - t0;              // first frame of this tile that is computed
                 if (tt_first > 0) {
                     const int stop = min(tt_first, rows);
-                    if (!psi_role) {
-                        // Row 0 of an empty-prefix extension, (x[0,c], logzero), is read back by the child's
-                        // first frame (its start is also 1), so it is written even when dead rows are skipped.
-                        if (t0 == 0 && plen == 0) rout[0] = make_float2(nb, E2E_CTC_LOGZERO);
-                        if (fill_dead)
-                            for (; tt < stop; ++tt)
-                                if (!(t0 + tt == 0 && plen == 0)) rout[(long long)(t0 + tt) * LU] = dead;
-                    }
+                    // Row 0 of an empty-prefix extension, (x[0,c], logzero), is read back by the child's
+                    // first frame (its start is also 1), so it is written even when dead rows are skipped.
+                    if (t0 == 0 && plen == 0) rout[0] = make_float2(nb, E2E_CTC_LOGZERO);
+                    if (fill_dead)
+                        for (; tt < stop; ++tt)
+                            if (!(t0 + tt == 0 && plen == 0)) rout[(long long)(t0 + tt) * LU] = dead;
                     tt = stop;
                 }
-                const float2 *php = ph_row + tt;
-                const float *xcp = xt + tt * pitch + col;
-                if (!psi_role) {
-                    // state thread: 3 LDS, 2 log-add-exp, 1 STG.64 per frame
-                    const float *xbp = kGather ? (xb_g + tt) : (xt + tt * pitch + E2E_CTC_BLANK);
-                    const int xb_step = kGather ? 1 : pitch;
-                    float2 *outp = rout + (long long)(t0 + tt) * LU;
-#pragma unroll 4
-                    for (; tt < rows; ++tt) {
-                        const float2 ph = *php;
-                        const float phi = special ? ph.y : ph.x;
-                        const float nnb = __fadd_rn(logaddexp<kMath>(nb, phi, lut), *xcp);
-                        const float nbl = __fadd_rn(logaddexp<kMath>(bl, nb, lut), *xbp);
-                        nb = nnb; bl = nbl;
-                        *outp = make_float2(nnb, nbl);
-                        ++php; xcp += pitch; xbp += xb_step; outp += LU;
-                    }
-                } else {
-                    // psi thread: 2 LDS, 1 log-add-exp per frame
-#pragma unroll 4
-                    for (; tt < rows; ++tt) {
-                        const float2 ph = *php;
-                        const float phi = special ? ph.y : ph.x;
-                        psi = logaddexp<kMath>(psi, __fadd_rn(phi, *xcp), lut);
-                        ++php; xcp += pitch;
-                    }
+                const float *php = phis + (size_t)(k & 1) * H * kPhiPitch + phi_col + 2 * tt;
+                xcp += tt * xc_step; xbp += tt * xb_step;
+                float2 *outp = rout + (long long)(t0 + tt) * LU;
+                // 3 LDS, 3 log-add-exp, 1 STG.64 per frame
+                auto frame = [&](int q) {
+                    const float ph = php[2 * q];
+                    const float xc = xcp[q * xc_step];
+                    const float xb = xbp[q * xb_step];
+                    const float nnb = __fadd_rn(logaddexp<kMath>(nb, ph, lut), xc);
+                    const float nbl = __fadd_rn(logaddexp<kMath>(bl, nb, lut), xb);
+                    psi = logaddexp<kMath>(psi, __fadd_rn(ph, xc), lut);
+                    nb = nnb; bl = nbl;
+                    outp[(long long)q * LU] = make_float2(nnb, nbl);
+                };
+                for (; tt + 4 <= rows; tt += 4) {
+                    frame(0); frame(1); frame(2); frame(3);
+                    php += 8; xcp += 4 * xc_step; xbp += 4 * xb_step; outp += 4LL * LU;
+                }
+                for (; tt < rows; ++tt) {
+                    frame(0);
+                    php += 2; xcp += xc_step; xbp += xb_step; outp += LU;
                 }
             }
-            if (k + 1 < n_tiles) phi_store(k + 1, pf);         // other phi buffer: nobody reads it before the next barrier
+            if (k + 1 < n_tiles) phi_convert(k + 1);           // other phi buffer: nobody reads it before the next barrier
         }
     }
 
     if (run) {
         const bool eos_lane = !full && tok == E2E_CTC_EOS;       // P(<eos> | g) = P(g)   (src/ctc.py:106-107)
-        if (eos_lane && (psi_role || (start >= T && fill_dead))) {
+        if (eos_lane) {
             const float2 a = __ldg(rprev_u + (long long)(T - 1) * p.lanes_prev + s_plane[h - h_lo]);
             psi = logaddexp<kMath>(a.x, a.y, lut);
             // psi aliases r[start-1,0,:] in the reference when the time loop never runs (src/ctc.py:85)
-            if (!psi_role) rout[(long long)(start - 1) * LU] = make_float2(psi, E2E_CTC_LOGZERO);
+            if (start >= T && fill_dead) rout[(long long)(start - 1) * LU] = make_float2(psi, E2E_CTC_LOGZERO);
         }
-        if (psi_role) p.psi[(long long)n * C + j] = psi;
-    } else if (active && psi_role) {
+        p.psi[(long long)n * C + j] = psi;
+    } else if (active) {
         p.psi[(long long)n * C + j] = E2E_CTC_LOGZERO;
     }
 }
 
 static size_t prefix_smem_bytes(bool gather, int lanes, int Vp, int H)
 {
-    size_t b = kLutBytes + prefix_xs_bytes(gather, lanes, Vp) + prefix_phis_bytes(H);
+    size_t b = kLutBytes + prefix_xs_bytes(gather, lanes, Vp) + prefix_phis_bytes(H) + prefix_stage_bytes(H);
     b = ((b + (size_t)(H + 2) * 4 + 7) & ~(size_t)7) + 16;
     return (b + 15) & ~(size_t)15;
+}
+
+typedef void (*PrefixKernel)(PrefixParams, CUtensorMap);
+
+// cuTensorMapEncodeTiled, fetched from the driver the process already has loaded (no link-time libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// Tensor map of the posterior tensor x [Tmax][U][Vp] (fp32) with a (Vp, 1, kTile) box.
+static int make_posterior_map(CUtensorMap *map, const float *x, int Tmax, int U, int Vp)
+{
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return set_error(E2E_ERR_LAUNCH, "e2e_ctc_prefix_score: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)Vp, (cuuint64_t)U, (cuuint64_t)Tmax};
+    const cuuint64_t strides[2] = {(cuuint64_t)Vp * 4, (cuuint64_t)U * Vp * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)Vp, 1u, (cuuint32_t)kTile};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(x), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(E2E_ERR_LAUNCH, "e2e_ctc_prefix_score: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return E2E_OK;
 }
 
 }  // namespace e2e
@@ -302,12 +365,17 @@ extern "C" int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int
         return set_error(E2E_ERR_ARG, "e2e_ctc_prefix_score: misaligned buffer");
 
     const long long LU = (long long)B * C;
+    if (n_run <= 0 || n_run > U) n_run = U;      // only the first n_run utterances are processed
     int nl = (int)((LU + 31) / 32 * 32);
     if (nl > kMaxLanes) {
         // split the utterance's lanes over several CTAs of equal, warp-multiple size
         const int chunks = (int)((LU + kMaxLanes - 1) / kMaxLanes);
         nl = (int)(((LU + chunks - 1) / chunks + 31) / 32 * 32);
     }
+    // A small launch cannot fill the machine and its duration is the longest utterance's chain:
+    // spread every utterance over one-warp CTAs so that each warp has a scheduler to itself.
+    // (Every lane computes the same values whatever the split.)
+    if (nl > 32 && (long long)n_run * ((LU + nl - 1) / nl) < 2 * 148) nl = 32;
     PrefixParams p;
     p.x = x; p.Tmax = Tmax; p.U = U; p.Vp = Vp; p.V = V; p.enc_len = enc_len;
     p.r_prev = reinterpret_cast<const float2 *>(r_prev); p.lanes_prev = lanes_prev;
@@ -318,26 +386,38 @@ extern "C" int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int
     p.chunks_per_utt = (int)((LU + nl - 1) / nl);
     p.hyps_per_cta = (nl + C - 1) / C + 1;
     if (p.hyps_per_cta > B) p.hyps_per_cta = B;
-    if (n_run <= 0 || n_run > U) n_run = U;      // only the first n_run utterances are processed
     const long long grid = (long long)n_run * p.chunks_per_utt;
     if (grid > 0x7fffffffLL) return set_error(E2E_ERR_UNSUPPORTED, "e2e_ctc_prefix_score: grid too large");
 
     const bool gather = Vp > kMaxRowFloats;
     const int math = (flags & E2E_PREFIX_FAST_MATH) ? kMathMufu : ((flags & E2E_PREFIX_LIBM_MATH) ? kMathLibm : kMathLut);
     const size_t smem = prefix_smem_bytes(gather, nl, Vp, p.hyps_per_cta);
-    void (*kern)(PrefixParams);
+    const bool fixed = !gather && Vp == 32 && LU == 96;      // char vocabulary, beam 8 (BASELINE cfg2)
+    const bool use_map = !gather && !(flags & E2E_PREFIX_ROW_COPIES);
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    if (use_map) {
+        const int rc = make_posterior_map(&map, x, Tmax, U, Vp);
+        if (rc != E2E_OK) return rc;
+    }
+    PrefixKernel kern;
     if (gather)
-        kern = math == kMathLut ? prefix_score_kernel<true, kMathLut>
-                                : (math == kMathMufu ? prefix_score_kernel<true, kMathMufu> : prefix_score_kernel<true, kMathLibm>);
+        kern = math == kMathLut ? prefix_score_kernel<true, kMathLut, 0, 0, false>
+                                : (math == kMathMufu ? prefix_score_kernel<true, kMathMufu, 0, 0, false> : prefix_score_kernel<true, kMathLibm, 0, 0, false>);
+    else if (!use_map)
+        kern = math == kMathLut ? prefix_score_kernel<false, kMathLut, 0, 0, false>
+                                : (math == kMathMufu ? prefix_score_kernel<false, kMathMufu, 0, 0, false> : prefix_score_kernel<false, kMathLibm, 0, 0, false>);
+    else if (fixed && math == kMathLut)
+        kern = prefix_score_kernel<false, kMathLut, 32, 96, true>;
     else
-        kern = math == kMathLut ? prefix_score_kernel<false, kMathLut>
-                                : (math == kMathMufu ? prefix_score_kernel<false, kMathMufu> : prefix_score_kernel<false, kMathLibm>);
+        kern = math == kMathLut ? prefix_score_kernel<false, kMathLut, 0, 0, true>
+                                : (math == kMathMufu ? prefix_score_kernel<false, kMathMufu, 0, 0, true> : prefix_score_kernel<false, kMathLibm, 0, 0, true>);
     if (smem > 48 * 1024) {
         if (smem > 200 * 1024) return set_error(E2E_ERR_UNSUPPORTED, "e2e_ctc_prefix_score: %zu bytes of shared memory needed", smem);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(E2E_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    kern<<<(unsigned)grid, 2 * nl, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    kern<<<(unsigned)grid, nl, smem, static_cast<cudaStream_t>(stream)>>>(p, map);
     count_launch();
     return check_launch("e2e_ctc_prefix_score");
 }

@@ -57,6 +57,8 @@ extern "C" {
 #define E2E_PREFIX_FAST_MATH      4 /* MUFU ex2/lg2 log-add-exp (abs. error ~3e-7) instead of the default
                                        table-based one (within one fp32 rounding of exact)              */
 #define E2E_PREFIX_LIBM_MATH      8 /* CUDA expf/log1pf log-add-exp: slow cross-check of the default     */
+#define E2E_PREFIX_ROW_COPIES    16 /* stage posterior tiles with one bulk copy per row instead of one
+                                       tensor-map box copy per tile (cross-check of the TMA path)       */
 
 /* flags of e2e_beam_combine_prune */
 #define E2E_BEAM_USE_CTC 1

@@ -56,7 +56,7 @@ def test_sass_uses_the_tma_engine_and_no_legacy_tensor_path():
         pytest.skip("cuobjdump not available")
     sass = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    assert "UBLKCP" in sass and "SYNCS" in sass
+    assert "UTMALDG" in sass and "UBLKCP" in sass and "SYNCS" in sass and "LDGSTS" in sass
     assert "HMMA" not in sass and "HGMMA" not in sass
 
 

@@ -145,6 +145,15 @@ def test_prefix_score_cfg2_shape(cuda, mode):
     print("cfg2-shape chain: max |gpu-oracle| = %.3g (math=%s)" % (w, mode))
 
 
+def test_prefix_score_row_copy_staging(cuda):
+    """E2E_PREFIX_ROW_COPIES: the per-row bulk-copy staging of the posterior tiles gives the same result as the
+    tensor-map box copy (both against the oracle)."""
+    _, L = _ops()
+    rng = np.random.default_rng(12)
+    _chain(cuda, rng, n_utts=5, t_lens=[180, 37, 96, 64, 181], vocab=31, beam=8, n_cand=12, n_steps=8, flags=L.PREFIX_ROW_COPIES)
+    _chain(cuda, rng, n_utts=3, t_lens=[50, 41, 7], vocab=200, beam=3, n_cand=4, n_steps=5, flags=L.PREFIX_ROW_COPIES)
+
+
 def test_prefix_score_skip_dead_rows(cuda):
     _, L = _ops()
     rng = np.random.default_rng(13)
@@ -161,6 +170,20 @@ def test_prefix_score_large_vocab_gather(cuda):
     rng = np.random.default_rng(15)
     w = _chain(cuda, rng, n_utts=2, t_lens=[60, 45], vocab=10000, beam=8, n_cand=12, n_steps=6)
     print("cfg3-shape chain (gather variant): max |gpu-oracle| = %.3g" % w)
+
+
+@pytest.mark.parametrize("vocab,beam,n_cand,flags", [(31, 8, 12, 0), (31, 8, 12, "skip"), (31, 16, 24, 0), (300, 8, 12, 0)])
+def test_prefix_score_machine_filling_launch(cuda, vocab, beam, n_cand, flags):
+    """>= 2 CTAs per SM: the kernel then runs its wide-CTA layout (up to 128 lanes per CTA; small launches are
+    split into one-warp CTAs), incl. the fixed-shape (Vp=32, 96 lanes) specialisation and the gather variant."""
+    _, L = _ops()
+    rng = np.random.default_rng(17)
+    n_utts = 320
+    t_lens = [int(t) for t in rng.integers(9, 70, n_utts)]
+    t_lens[0], t_lens[1] = 97, 5
+    fl = L.PREFIX_SKIP_DEAD_ROWS if flags == "skip" else 0
+    w = _chain(cuda, rng, n_utts=n_utts, t_lens=t_lens, vocab=vocab, beam=beam, n_cand=n_cand, n_steps=4, flags=fl)
+    print("machine-filling launch V=%d B=%d: max |gpu-oracle| = %.3g" % (vocab, beam, w))
 
 
 def test_prefix_score_midsize_vocab_rows(cuda):
