@@ -207,5 +207,38 @@ def attention_loc_full(key, value, query, prev_att, enc_len, w_conv, w_proj, w_e
     return attn, ctx
 
 
+def lstm_split_rows(src, row_idx, n, dst, k, off):
+    """dst[r, p*k + off : p*k + off + w] = p-th bf16 piece of src[row_idx[r]] (src [*,w] fp32, dst [>=n, 3k] bf16)."""
+    _chk(src, F32, "src")
+    _chk(row_idx, torch.int64, "row_idx", n)
+    _chk(dst, torch.bfloat16, "dst")
+    w = src.shape[1]
+    if dst.shape[0] < n or dst.shape[1] < 3 * k:
+        raise ValueError("lstm_split_rows: dst too small")
+    if row_idx is None and src.shape[0] < n:
+        raise ValueError("lstm_split_rows: src has fewer than n rows")
+    L.check(L.load().e2e_lstm_split_rows(L.ptr(src), int(src.stride(0)), L.ptr(row_idx), int(n), int(w),
+                                        L.ptr(dst), int(dst.stride(0)), int(k), int(off), _stream()))
+
+
+def lstm_cell(gates, bias, c_prev, row_idx, n, c_new, h_new, table=None, tok=None, a_next=None, k_next=0, off_next=0):
+    """Fused LSTM cell (see e2e_lstm_cell): gates [>=n,4D] fp32 -> c_new, h_new [>=n,D] (+ split of h into a_next)."""
+    _chk(gates, F32, "gates")
+    _chk(bias, F32, "bias")
+    _chk(c_prev, F32, "c_prev")
+    _chk(row_idx, torch.int64, "row_idx", n)
+    _chk(c_new, F32, "c_new")
+    _chk(h_new, F32, "h_new")
+    _chk(table, F32, "table")
+    _chk(tok, torch.int64, "tok", n)
+    _chk(a_next, torch.bfloat16, "a_next")
+    d = c_prev.shape[1]
+    if gates.shape[0] < n or gates.shape[1] < 4 * d or c_new.shape[0] < n or h_new.shape[0] < n or bias.numel() < 4 * d:
+        raise ValueError("lstm_cell: inconsistent shapes")
+    L.check(L.load().e2e_lstm_cell(L.ptr(gates), int(gates.stride(0)), L.ptr(bias), L.ptr(table), L.ptr(tok), L.ptr(c_prev),
+                                  L.ptr(row_idx), int(n), int(d), L.ptr(c_new), L.ptr(h_new), L.ptr(a_next),
+                                  int(a_next.stride(0)) if a_next is not None else 0, int(k_next), int(off_next), _stream()))
+
+
 def launch_count():
     return int(L.load().e2e_launch_count())

@@ -135,6 +135,70 @@ class _Rnn:
         return ([t.index_select(0, idx) for t in h], [t.index_select(0, idx) for t in c] if c is not None else None)
 
 
+class _FusedLstm:
+    """n-layer LSTM advanced one token at a time for a batch of rows, entirely on the device path
+    (SURVEY §8f row f-2): per layer one hand-written split kernel, the three split GEMMs (library,
+    tensor cores, fp32 accumulation) and one hand-written cell kernel (csrc/lstm_step.cu).  States
+    are never permuted: a step reads the previous states through the parents' row index ``idx``
+    and writes the new ones to the other half of a ping-pong buffer."""
+
+    def __init__(self, rnn, first_input_table=None):
+        self.layers, self.dim = rnn.num_layers, rnn.hidden_size
+        self.lin, self.bias, self.k_in, self.table0 = [], [], [], None
+        for l in range(self.layers):
+            w_ih, w_hh, b_ih, b_hh = (getattr(rnn, "{}_l{}".format(k, l)).detach().float()
+                                      for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+            if l == 0 and first_input_table is not None:
+                # layer 0 sees one of V embeddings: its input projection is a [V, 4D] table
+                self.table0 = (first_input_table.double() @ w_ih.double().t() + b_ih.double()).float().contiguous()
+                self.lin.append(SplitLinear(w_hh))
+                self.bias.append(b_hh.contiguous())
+                self.k_in.append(0)
+            else:
+                self.lin.append(SplitLinear(torch.cat([w_ih, w_hh], dim=1)))
+                self.bias.append((b_ih + b_hh).contiguous())
+                self.k_in.append(w_ih.shape[1])
+        self.cur = 0
+
+    def start(self, n, device):
+        d = self.dim
+        self.h = [[torch.zeros(n, d, device=device) for _ in range(self.layers)] for _ in range(2)]
+        self.c = [[torch.zeros(n, d, device=device) for _ in range(self.layers)] for _ in range(2)]
+        self.a = [torch.empty(n, 3 * (self.k_in[l] + d), dtype=torch.bfloat16, device=device) for l in range(self.layers)]
+        self.idx = torch.arange(n, device=device)
+        self.cur = 0
+
+    def hidden(self, n):
+        """[n, layers*D] hidden states of the rows' parents (what Decoder.get_query reads, asr.py:251-254)."""
+        hs = [h.index_select(0, self.idx[:n]) for h in self.h[self.cur]]
+        return hs[0] if len(hs) == 1 else torch.cat(hs, dim=1)
+
+    def step(self, n, x0=None, tok=None):
+        """Advance rows [:n]; x0 [n, in] fp32 (or tok [n] for a tabled layer 0) -> top hidden [n, D]."""
+        from . import ops
+        cur, new, d = self.cur, 1 - self.cur, self.dim
+        idx = self.idx
+        for l in range(self.layers):                                   # recurrent halves of the A operands
+            ops.lstm_split_rows(self.h[cur][l], idx, n, self.a[l], self.k_in[l] + d, self.k_in[l])
+        if self.k_in[0] > 0:
+            ops.lstm_split_rows(x0.contiguous(), None, n, self.a[0], self.k_in[0] + d, 0)
+        for l in range(self.layers):
+            k = self.k_in[l] + d
+            a, lin = self.a[l][:n], self.lin[l]
+            y = torch.mm(a, lin.b2, out_dtype=torch.float32)
+            y = torch.addmm(y, a[:, :2 * k], lin.b1, out_dtype=torch.float32)
+            y = torch.addmm(y, a[:, :k], lin.b0, out_dtype=torch.float32)
+            nxt = l + 1 < self.layers
+            ops.lstm_cell(y, self.bias[l], self.c[cur][l], idx, n, self.c[new][l], self.h[new][l],
+                          table=self.table0 if l == 0 else None, tok=tok if (l == 0 and self.table0 is not None) else None,
+                          a_next=self.a[l + 1] if nxt else None, k_next=(self.k_in[l + 1] + d) if nxt else 0, off_next=0)
+        self.cur = new
+        return self.h[new][self.layers - 1][:n]
+
+    def reorder(self, idx):
+        self.idx = idx
+
+
 class BatchedStepper:
     def __init__(self, asr, lm=None, split_gemm=False, fused_attention=False):
         att = asr.attention
@@ -144,8 +208,15 @@ class BatchedStepper:
             raise NotImplementedError("attention mode " + str(att.mode))
         self.asr, self.lm = asr, lm
         self.mode, self.temperature = att.mode, att.att_layer.temperature
-        self.dec = _Rnn(asr.decoder.layers, split_gemm)
-        self.lm_rnn = _Rnn(lm.rnn, split_gemm, lm.emb.weight.detach()) if lm is not None else None
+        # fused device LSTM steps (csrc/lstm_step.cu) whenever the weights live on a GPU; the plain
+        # PyTorch cells otherwise (CPU tests of the host logic, GRU models)
+        def make(rnn, table=None):
+            on_gpu = next(rnn.parameters()).is_cuda
+            if split_gemm and on_gpu and isinstance(rnn, torch.nn.LSTM):
+                return _FusedLstm(rnn, table)
+            return _Rnn(rnn, split_gemm, table)
+        self.dec = make(asr.decoder.layers)
+        self.lm_rnn = make(lm.rnn, lm.emb.weight.detach()) if lm is not None else None
         self.mark = lambda name: None            # profiling hook (decode.py sets it)
         self.fused_attention = False
         if fused_attention and self.mode == "loc":
@@ -208,8 +279,16 @@ class BatchedStepper:
             self.prev_att = uni[:, None, :].expand(u, beam, t).reshape(self.N, t).contiguous()
         else:
             self.prev_att = None
-        self.dec_state = self.dec.zeros(self.N, dev)
-        self.lm_state = self.lm_rnn.zeros(self.N, dev) if self.lm_rnn is not None else None
+        self.dec_fused = isinstance(self.dec, _FusedLstm)
+        self.lm_fused = isinstance(self.lm_rnn, _FusedLstm)
+        if self.dec_fused:
+            self.dec.start(self.N, dev)
+        else:
+            self.dec_state = self.dec.zeros(self.N, dev)
+        if self.lm_fused:
+            self.lm_rnn.start(self.N, dev)
+        else:
+            self.lm_state = self.lm_rnn.zeros(self.N, dev) if self.lm_rnn is not None else None
         self._base = torch.arange(u, device=dev, dtype=torch.long)[:, None] * beam
         self._enc_len32 = enc_len.to(torch.int32).contiguous()
 
@@ -223,7 +302,8 @@ class BatchedStepper:
         b, t = self.B, self.T
         n = k * b
         self._k = k
-        query = torch.tanh(att.proj_q(torch.cat([h[:n] for h in self.dec_state[0]], dim=1)))   # asr.py:337 / :251-254
+        dec_h = self.dec.hidden(n) if self.dec_fused else torch.cat([h[:n] for h in self.dec_state[0]], dim=1)
+        query = torch.tanh(att.proj_q(dec_h))                                              # asr.py:337 / :251-254
         if self.mode == "loc" and self.fused_attention:
             from . import ops
             # conv + energies + masked softmax + context in one kernel (csrc/attention_full.cu)
@@ -244,14 +324,20 @@ class BatchedStepper:
             context = torch.bmm(attn, self.value[:k]).view(n, -1)                      # module.py:1114
         self.mark("step_attention")
         dec_in = torch.cat([asr.pre_embed(prev_tok), context], dim=-1)             # decode.py:114-115
-        top, self._new_dec = self.dec.step(dec_in, self.dec_state, n)
+        if self.dec_fused:
+            top = self.dec.step(n, x0=dec_in)
+        else:
+            top, self._new_dec = self.dec.step(dec_in, self.dec_state, n)
         att_logits = asr.decoder.char_trans(top)                                   # asr.py:265
         self._new_att = attn.view(n, t) if self.mode == "loc" else None
         self.mark("step_speller")
         lm_logits = None
         if self.lm is not None:
             x0 = None if self.lm_rnn.table0 is not None else self.lm.emb(prev_tok)
-            top, self._new_lm = self.lm_rnn.step(x0, self.lm_state, n, tok=prev_tok)
+            if self.lm_fused:
+                top = self.lm_rnn.step(n, x0=x0, tok=prev_tok)
+            else:
+                top, self._new_lm = self.lm_rnn.step(x0, self.lm_state, n, tok=prev_tok)
             lm_logits = F.linear(top, self.lm.emb.weight) if self.lm.emb_tying else self.lm.trans(top)   # lm.py:33-37
             self.mark("step_lm")
         return att_logits.contiguous(), (lm_logits.contiguous() if lm_logits is not None else None)
@@ -262,8 +348,14 @@ class BatchedStepper:
         utterances advanced by the last :meth:`step` are touched."""
         k = self._k
         idx = (self._base[:k] + parent_slot[:k].long()).reshape(-1)
-        self.dec_state = _Rnn.gather(self._new_dec, idx)
+        if self.dec_fused:
+            self.dec.reorder(idx)
+        else:
+            self.dec_state = _Rnn.gather(self._new_dec, idx)
         if self._new_att is not None:
             self.prev_att = self._new_att.index_select(0, idx)
         if self.lm is not None:
-            self.lm_state = _Rnn.gather(self._new_lm, idx)
+            if self.lm_fused:
+                self.lm_rnn.reorder(idx)
+            else:
+                self.lm_state = _Rnn.gather(self._new_lm, idx)

@@ -192,6 +192,30 @@ int e2e_attention_loc_full(const float *key, const float *value, const float *qu
                            float b_energy, float temperature, int n_run, int B, int T, int A, int K, int W, int E,
                            int hyps_per_cta, float *attn, float *ctx, void *stream);
 
+/* (next) One-token LSTM step of the batched RNNLM (src/lm.py:27-38: nn.LSTM on a
+ * [1,1] token) and speller (src/asr.py:259-266).  The recurrent GEMMs stay library calls on an exact 3-piece
+ * bf16 split of the fp32 operands; these two entry points are everything around them.
+ *
+ * e2e_lstm_split_rows: dst[r][p*K + off + c] = piece_p(src[row(r)][c]) for p = 0,1,2 and c < w, where
+ *   x = piece_0 + piece_1 + piece_2 exactly (piece_0 = bf16(x), piece_1 = bf16(x - piece_0), ...),
+ *   row(r) = row_idx ? row_idx[r] : r   (row_idx: int64, the surviving hypotheses' parent rows —
+ *   the state hand-over of src/decode.py:250-257 without copying states).
+ *   src fp32 [*][src_pitch]; dst bf16 [n][dst_pitch], dst_pitch >= 3*K: the A operand [a1 | a2 | a3] of the GEMMs. */
+int e2e_lstm_split_rows(const float *src, long long src_pitch, const long long *row_idx, int n, int w,
+                        void *dst_bf16, long long dst_pitch, int K, int off, void *stream);
+
+/* e2e_lstm_cell: z = gates[r] + bias (+ table[tok[r]]), gate order i,f,g,o (torch.nn.LSTM);
+ *   c'[r] = sigmoid(z_f) * c_prev[row(r)] + sigmoid(z_i) * tanh(z_g);  h'[r] = sigmoid(z_o) * tanh(c'[r])
+ *   (fp32, every product and sum rounded separately like the reference's element-wise ops), and, if
+ *   a_next_bf16 is given, the 3-piece split of h'[r] into columns [off_next, off_next+D) of the next
+ *   layer's A operand (geometry as above).
+ *   gates fp32 [n][gates_pitch >= 4D]; bias [4D] (b_ih + b_hh); table [V][4D] + tok int64 [n] (the
+ *   layer-0 input projection of the V possible embeddings) or NULL; c_prev [*][D]; c_new, h_new [n][D]. */
+int e2e_lstm_cell(const float *gates, long long gates_pitch, const float *bias, const float *table, const long long *tok,
+                  const float *c_prev, const long long *row_idx, int n, int D,
+                  float *c_new, float *h_new, void *a_next_bf16, long long a_pitch, int K_next, int off_next,
+                  void *stream);
+
 /* Number of kernel launches issued through this library by the calling process
  * (for bench.py's gpu_launches claim). */
 long long e2e_launch_count(void);

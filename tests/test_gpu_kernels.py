@@ -334,3 +334,91 @@ def test_attention_loc_full_matches_oracle(cuda, n_utts, beam, t_len, dim, n_fil
         ops.attention_loc_full(dev(key), dev(value), dev(query), dev(prev), dev(enc_len), dev(conv_w), dev(w_proj), dev(w_e),
                                0.25, 0.5, beam, n_run=1, attn=attn, ctx=ctx)
         assert torch.equal(attn[:beam].cpu(), got_a[:beam]) and (attn[beam:] == -7.0).all() and (ctx[beam:] == -7.0).all()
+
+
+# ----------------------------------------------------------------------------------------------
+# f-2: LSTM step kernels
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,w,k,off,gather", [(37, 1024, 2048, 1024, True), (5, 940, 1240, 0, False), (3, 300, 1240, 940, True), (2, 7, 9, 1, True)])
+def test_lstm_split_rows_is_the_exact_three_piece_split(cuda, n, w, k, off, gather):
+    """Pieces bit-equal to the torch restatement bf16(x), bf16(x - a1), bf16(x - a1 - a2); rows gathered through
+    the parent index; columns outside the slot untouched."""
+    ops, _ = _ops()
+    from e2e_asr_pytorch_b200.stepper import _split3
+    g = torch.Generator().manual_seed(n + w)
+    src = (torch.randn(n + 4, w, generator=g) * 3).to(cuda)
+    idx = torch.randint(0, n + 4, (n,), generator=g).to(cuda) if gather else None
+    dst = torch.full((n + 1, 3 * k), 7.0, dtype=torch.bfloat16, device=cuda)
+    ops.lstm_split_rows(src, idx, n, dst, k, off)
+    rows = src.index_select(0, idx) if gather else src[:n]
+    want = _split3(rows)
+    for p in range(3):
+        assert torch.equal(dst[:n, p * k + off:p * k + off + w], want[p])
+    mask = torch.ones(3 * k, dtype=torch.bool)
+    for p in range(3):
+        mask[p * k + off:p * k + off + w] = False
+    assert (dst[:n][:, mask.to(cuda)] == 7.0).all() and (dst[n] == 7.0).all()
+    back = want[0].float() + (want[1].float() + want[2].float())
+    assert (back - rows).abs().max().item() <= 2e-7 * rows.abs().max().item()
+
+
+@pytest.mark.parametrize("n,d,with_table,with_next", [(33, 1024, True, True), (9, 300, False, False), (4, 12, True, False)])
+def test_lstm_cell_matches_torch(cuda, n, d, with_table, with_next):
+    """c', h' within 1e-6 abs of a float64 evaluation of the nn.LSTM cell; the split of h' lands in the next
+    layer's operand."""
+    ops, _ = _ops()
+    from e2e_asr_pytorch_b200.stepper import _split3
+    g = torch.Generator().manual_seed(d)
+    gates = torch.randn(n, 4 * d, generator=g) * 2
+    bias = torch.randn(4 * d, generator=g)
+    table = torch.randn(5, 4 * d, generator=g) if with_table else None
+    tok = torch.randint(0, 5, (n,), generator=g) if with_table else None
+    c_prev = torch.randn(n + 3, d, generator=g)
+    idx = torch.randint(0, n + 3, (n,), generator=g)
+    z = gates.double() + bias.double() + (table.double()[tok] if with_table else 0)
+    i, f, gg, o = z.chunk(4, dim=-1)
+    c_want = torch.sigmoid(f) * c_prev.double()[idx] + torch.sigmoid(i) * torch.tanh(gg)
+    h_want = torch.sigmoid(o) * torch.tanh(c_want)
+    dev = lambda t: None if t is None else t.to(cuda)
+    c_new, h_new = torch.empty(n, d, device=cuda), torch.empty(n, d, device=cuda)
+    k_next = 2 * d
+    a_next = torch.zeros(n, 3 * k_next, dtype=torch.bfloat16, device=cuda) if with_next else None
+    ops.lstm_cell(dev(gates), dev(bias), dev(c_prev), dev(idx), n, c_new, h_new, table=dev(table), tok=dev(tok),
+                  a_next=a_next, k_next=k_next if with_next else 0, off_next=0)
+    assert (c_new.cpu().double() - c_want).abs().max().item() < 1e-6
+    assert (h_new.cpu().double() - h_want).abs().max().item() < 1e-6
+    if with_next:
+        want = _split3(h_new)
+        for p in range(3):
+            assert torch.equal(a_next[:, p * k_next:p * k_next + d], want[p])
+
+
+def test_fused_lstm_stack_matches_nn_lstm(cuda):
+    """Three steps of the device LSTM stack (split kernel + split GEMMs + cell kernel, states read through the
+    parents' row index) against torch.nn.LSTM in float64 fed with the same parent permutation."""
+    _ops()
+    from e2e_asr_pytorch_b200.stepper import _FusedLstm
+    from e2e_asr_pytorch_b200.decode import _Fp32Math
+    torch.manual_seed(3)
+    for in_dim, d, layers, table in [(24, 16, 2, False), (16, 16, 3, True)]:
+        rnn = torch.nn.LSTM(in_dim, d, num_layers=layers, batch_first=True)
+        emb = torch.randn(7, in_dim)
+        ref = torch.nn.LSTM(in_dim, d, num_layers=layers, batch_first=True).double()
+        ref.load_state_dict({k: v.double() for k, v in rnn.state_dict().items()})
+        n = 10
+        with torch.no_grad(), _Fp32Math():
+            fused = _FusedLstm(rnn.to(cuda), emb.to(cuda) if table else None)
+            fused.start(n, cuda)
+            h = torch.zeros(layers, n, d, dtype=torch.float64)
+            c = torch.zeros(layers, n, d, dtype=torch.float64)
+            g = torch.Generator().manual_seed(5)
+            for step in range(3):
+                tok = torch.randint(0, 7, (n,), generator=g)
+                x = emb[tok] if table else torch.randn(n, in_dim, generator=g)
+                top = fused.step(n, x0=None if table else x.to(cuda), tok=tok.to(cuda) if table else None)
+                out, (h, c) = ref(x.double()[:, None, :], (h, c))
+                assert (top.cpu().double() - out[:, 0]).abs().max().item() < 2e-6
+                perm = torch.randint(0, n, (n,), generator=g)           # survivors pick parents
+                fused.reorder(perm.to(cuda))
+                h, c = h[:, perm], c[:, perm]
+                assert (fused.hidden(n).cpu().double() - torch.cat(list(h), dim=1)).abs().max().item() < 2e-6
