@@ -9,14 +9,15 @@
 // the previous alignments and the queries, and writes the new alignments and contexts.
 //
 // Mapping: one CTA per (utterance, group of NB beam slots), one THREAD per encoder frame t
-// (256 frames per pass) that carries the NB hypotheses of the group together, so a key row is
-// fetched once per group and the per-channel constants (loc_proj row, gen_energy weight, the
+// (256 frames per pass) that carries the NB hypotheses of the group together, so a key value is
+// fetched once per group (the keys arrive channel-major, key_t[u][a][t], so the warp's 32 frames
+// are one coalesced 128-byte load per channel) and the per-channel constants (loc_proj row, gen_energy weight, the
 // NB queries) are shared-memory broadcasts.  Frames t >= enc_len[u] are never touched: a batch
 // padded to the longest utterance costs nothing.  tanh(x) = 1 - 2/(1 + exp(2x)) through
 // MUFU.EX2 + MUFU.RCP (absolute error ~2e-7); the kernel is MUFU-bound by construction
 // (4 MUFU per (hypothesis, frame, channel)).
-// The context product runs in the same CTA afterwards: thread <-> output column e, the NB
-// alignments are read as one broadcast LDS.128 per frame, value rows are coalesced.
+// The context product runs in the same CTA afterwards: thread <-> 4 output columns (16-byte
+// loads, 4 frames in flight), the NB alignments are read as one broadcast LDS.128 per frame.
 // Results do not depend on NB (every hypothesis sees the same operations in the same order),
 // so the host picks NB by launch size only.
 #include "common.cuh"
@@ -35,7 +36,7 @@ __device__ __forceinline__ float af_tanh(float x)
 }
 
 struct AttFullParams {
-    const float *key, *value, *query, *prev_att; const int *enc_len;
+    const float *key_t, *value, *query, *prev_att; const int *enc_len;
     const float *w_conv, *w_proj, *w_energy; float b_energy, temperature;
     int B, T, A, K, W, E, groups;
     float *attn, *ctx;
@@ -115,13 +116,14 @@ attention_full_kernel(const AttFullParams p)
                     for (int k = 0; k < KP; ++k) f[b][k] = fmaf(wj[k], a, f[b][k]);
                 }
             }
-            const float4 *krow = reinterpret_cast<const float4 *>(p.key + ((size_t)u * T + t) * A);
+            const float *kcol = p.key_t + (size_t)u * A * T + t;        // key_t[u][a][t]: coalesced across the warp's frames
             float acc[NB];
 #pragma unroll
             for (int b = 0; b < NB; ++b) acc[b] = p.b_energy;
             for (int a4 = 0; a4 < A / 4; ++a4) {
-                const float4 kv = __ldg(krow + a4);
-                const float kk[4] = {kv.x, kv.y, kv.z, kv.w};
+                float kk[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) kk[i] = __ldg(kcol + (size_t)(a4 * 4 + i) * T);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float4 *c = cst + (a4 * 4 + i) * 5;
@@ -180,30 +182,59 @@ attention_full_kernel(const AttFullParams p)
     }
 
     // ---- context: ctx[b][e] = sum_t attn[b][t] * value[u][t][e]  (module.py:1114) -------------------
+    // thread <-> 4 consecutive columns (one 16-byte load per frame, whole row coalesced), 4 frames in flight
     const float *vbase = p.value + (size_t)u * T * p.E;
-    for (int e = tid; e < p.E; e += kAfThreads) {
-        float acc[NB];
+    if ((p.E & 3) == 0) {
+        for (int e = tid * 4; e < p.E; e += kAfThreads * 4) {
+            float acc[NB][4];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) acc[b] = 0.0f;
-        const float *vp = vbase + e;
-        int t = 0;
-        for (; t + 4 <= Tu; t += 4) {
-            float v[4];
+            for (int b = 0; b < NB; ++b)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = __ldg(vp + (size_t)(t + q) * p.E);
+                for (int i = 0; i < 4; ++i) acc[b][i] = 0.0f;
+            const float *vp = vbase + e;
+            int t = 0;
+            for (; t + 4 <= Tu; t += 4) {
+                float4 v[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const float4 *>(vp + (size_t)(t + q) * p.E));
 #pragma unroll
-                for (int b = 0; b < NB; ++b) acc[b] = fmaf(es[(t + q) * NB + b], v[q], acc[b]);
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        const float a = es[(t + q) * NB + b];
+                        acc[b][0] = fmaf(a, v[q].x, acc[b][0]); acc[b][1] = fmaf(a, v[q].y, acc[b][1]);
+                        acc[b][2] = fmaf(a, v[q].z, acc[b][2]); acc[b][3] = fmaf(a, v[q].w, acc[b][3]);
+                    }
+            }
+            for (; t < Tu; ++t) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(vp + (size_t)t * p.E));
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const float a = es[t * NB + b];
+                    acc[b][0] = fmaf(a, v.x, acc[b][0]); acc[b][1] = fmaf(a, v.y, acc[b][1]);
+                    acc[b][2] = fmaf(a, v.z, acc[b][2]); acc[b][3] = fmaf(a, v.w, acc[b][3]);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+                if (b0 + b < p.B)
+                    *reinterpret_cast<float4 *>(p.ctx + ((size_t)u * p.B + b0 + b) * p.E + e) = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
         }
-        for (; t < Tu; ++t) {
-            const float v = __ldg(vp + (size_t)t * p.E);
+    } else {
+        for (int e = tid; e < p.E; e += kAfThreads) {
+            float acc[NB];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) acc[b] = fmaf(es[t * NB + b], v, acc[b]);
+            for (int b = 0; b < NB; ++b) acc[b] = 0.0f;
+            const float *vp = vbase + e;
+            for (int t = 0; t < Tu; ++t) {
+                const float v = __ldg(vp + (size_t)t * p.E);
+#pragma unroll
+                for (int b = 0; b < NB; ++b) acc[b] = fmaf(es[t * NB + b], v, acc[b]);
+            }
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+                if (b0 + b < p.B) p.ctx[((size_t)u * p.B + b0 + b) * p.E + e] = acc[b];
         }
-#pragma unroll
-        for (int b = 0; b < NB; ++b)
-            if (b0 + b < p.B) p.ctx[((size_t)u * p.B + b0 + b) * p.E + e] = acc[b];
     }
 }
 
@@ -236,18 +267,19 @@ static int att_full_launch(const AttFullParams &p, int KP, int n_run, cudaStream
 
 }  // namespace e2e
 
-extern "C" int e2e_attention_loc_full(const float *key, const float *value, const float *query, const float *prev_att,
+extern "C" int e2e_attention_loc_full(const float *key_t, const float *value, const float *query, const float *prev_att,
                                       const int *enc_len, const float *w_conv, const float *w_proj, const float *w_energy,
                                       float b_energy, float temperature, int n_run, int B, int T, int A, int K, int W, int E,
                                       int hyps_per_cta, float *attn, float *ctx, void *stream)
 {
     using namespace e2e;
-    if (!key || !value || !query || !prev_att || !enc_len || !w_conv || !w_proj || !w_energy || !attn || !ctx)
+    if (!key_t || !value || !query || !prev_att || !enc_len || !w_conv || !w_proj || !w_energy || !attn || !ctx)
         return set_error(E2E_ERR_ARG, "e2e_attention_loc_full: null pointer");
     if (n_run <= 0 || B <= 0 || T <= 0 || A <= 0 || K <= 0 || W <= 0 || E <= 0) return set_error(E2E_ERR_ARG, "e2e_attention_loc_full: bad size");
     if (K > kAfMaxK || (A & 3) != 0 || (W & 1) == 0)
         return set_error(E2E_ERR_UNSUPPORTED, "e2e_attention_loc_full: needs loc_kernel_num <= 12, dim %% 4 == 0 and an odd filter length");
-    if (reinterpret_cast<uintptr_t>(key) & 15) return set_error(E2E_ERR_ARG, "e2e_attention_loc_full: key must be 16-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(value) & 15) || (reinterpret_cast<uintptr_t>(ctx) & 15))
+        return set_error(E2E_ERR_ARG, "e2e_attention_loc_full: value and ctx must be 16-byte aligned");
     int NB = hyps_per_cta;
     if (NB <= 0) {   // by launch size: enough CTAs to cover the machine, otherwise as much key reuse as possible
         const long long want = 2LL * 148;
@@ -256,7 +288,7 @@ extern "C" int e2e_attention_loc_full(const float *key, const float *value, cons
     if (NB != 1 && NB != 2 && NB != 4) return set_error(E2E_ERR_ARG, "e2e_attention_loc_full: hyps_per_cta must be 0, 1, 2 or 4");
     while (NB > 1 && NB / 2 >= B) NB /= 2;
     AttFullParams p;
-    p.key = key; p.value = value; p.query = query; p.prev_att = prev_att; p.enc_len = enc_len;
+    p.key_t = key_t; p.value = value; p.query = query; p.prev_att = prev_att; p.enc_len = enc_len;
     p.w_conv = w_conv; p.w_proj = w_proj; p.w_energy = w_energy; p.b_energy = b_energy; p.temperature = temperature;
     p.B = B; p.T = T; p.A = A; p.K = K; p.W = W; p.E = E; p.groups = (B + NB - 1) / NB;
     p.attn = attn; p.ctx = ctx;

@@ -176,16 +176,16 @@ def attention_loc_step(key, query, loc_feat, enc_len, w_proj, w_energy, b_energy
     return attn
 
 
-def attention_loc_full(key, value, query, prev_att, enc_len, w_conv, w_proj, w_energy, b_energy, temperature, beam,
+def attention_loc_full(key_t, value, query, prev_att, enc_len, w_conv, w_proj, w_energy, b_energy, temperature, beam,
                        n_run=None, hyps_per_cta=0, attn=None, ctx=None):
     """The whole location-aware attention step (conv + energies + masked softmax + context) for the first
-    ``n_run`` utterances: key [U,T,A], value [U,T,E], query [>=n_run*B,A], prev_att [>=n_run*B,T],
-    w_conv [K,W] -> (attn [n_run*B,T], ctx [n_run*B,E])."""
-    for t, nm in ((key, "key"), (value, "value"), (query, "query"), (prev_att, "prev_att"), (w_conv, "w_conv"),
+    ``n_run`` utterances: key_t [U,A,T] (channel-major keys), value [U,T,E], query [>=n_run*B,A],
+    prev_att [>=n_run*B,T], w_conv [K,W] -> (attn [n_run*B,T], ctx [n_run*B,E])."""
+    for t, nm in ((key_t, "key_t"), (value, "value"), (query, "query"), (prev_att, "prev_att"), (w_conv, "w_conv"),
                   (w_proj, "w_proj"), (w_energy, "w_energy")):
         _chk(t, F32, nm)
     _chk(enc_len, I32, "enc_len")
-    u, t_len, a = key.shape
+    u, a, t_len = key_t.shape
     e = value.shape[2]
     k, w = w_conv.shape
     n_run = u if n_run is None else int(n_run)
@@ -195,12 +195,12 @@ def attention_loc_full(key, value, query, prev_att, enc_len, w_conv, w_proj, w_e
     _chk(query, F32, "query", n * a)
     _chk(prev_att, F32, "prev_att", n * t_len)
     if attn is None:
-        attn = torch.empty((n, t_len), dtype=F32, device=key.device)
+        attn = torch.empty((n, t_len), dtype=F32, device=key_t.device)
     if ctx is None:
-        ctx = torch.empty((n, e), dtype=F32, device=key.device)
+        ctx = torch.empty((n, e), dtype=F32, device=key_t.device)
     _chk(attn, F32, "attn", n * t_len)
     _chk(ctx, F32, "ctx", n * e)
-    L.check(L.load().e2e_attention_loc_full(L.ptr(key), L.ptr(value), L.ptr(query), L.ptr(prev_att), L.ptr(enc_len),
+    L.check(L.load().e2e_attention_loc_full(L.ptr(key_t), L.ptr(value), L.ptr(query), L.ptr(prev_att), L.ptr(enc_len),
                                            L.ptr(w_conv), L.ptr(w_proj), L.ptr(w_energy), float(b_energy), float(temperature),
                                            n_run, int(beam), int(t_len), int(a), int(k), int(w), int(e), int(hyps_per_cta),
                                            L.ptr(attn), L.ptr(ctx), _stream()))

@@ -272,6 +272,9 @@ class BatchedStepper:
         self.U, self.B, self.T, self.N = u, beam, t, u * beam
         dev = enc.device
         self.key = torch.tanh(att.proj_k(enc))                                   # [U,T,A]   asr.py:343
+        if self.fused_attention:
+            self.key_t = self.key.transpose(1, 2).contiguous()                   # [U,A,T] channel-major for the fused kernel
+            self.key = None
         self.value = torch.tanh(att.proj_v(enc)) if att.v_proj else enc          # [U,T,E]
         self.pad = torch.arange(t, device=dev)[None, :] >= enc_len[:, None]      # [U,T]     module.py:1100-1107
         if self.mode == "loc":
@@ -307,7 +310,7 @@ class BatchedStepper:
         if self.mode == "loc" and self.fused_attention:
             from . import ops
             # conv + energies + masked softmax + context in one kernel (csrc/attention_full.cu)
-            attn, context = ops.attention_loc_full(self.key, self.value, query.contiguous(), self.prev_att, self._enc_len32,
+            attn, context = ops.attention_loc_full(self.key_t, self.value, query.contiguous(), self.prev_att, self._enc_len32,
                                                    self._w_conv, self._w_proj, self._w_energy, self._b_energy,
                                                    self.temperature, b, n_run=k)
         else:

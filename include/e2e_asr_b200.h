@@ -183,11 +183,12 @@ int e2e_attention_loc_step(const float *key, const float *query, const float *lo
  *   feat[n][k][t] = sum_j w_conv[k][j] * prev_att[n][t + j - W/2]
  *   attn[n][t]    = as e2e_attention_loc_step, from feat;   exactly 0 for t >= enc_len[u]
  *   ctx[n][e]     = sum_{t < enc_len[u]} attn[n][t] * value[u][t][e]
- *   key [U][T][A], value [U][T][E], query [n][A], prev_att [n][T] (zero beyond enc_len[u]),
+ *   key_t [U][A][T] (the keys tanh(proj_k(enc)), src/asr.py:343, stored CHANNEL-major), value [U][T][E],
+ *   query [n][A], prev_att [n][T] (zero beyond enc_len[u]),
  *   w_conv [K][W], w_proj [A][K], w_energy [A]; attn [n][T], ctx [n][E].
  *   hyps_per_cta: 0 (choose by launch size) or 1, 2, 4 — the result does not depend on it.
  *   Needs K <= 12, A % 4 == 0, W odd. */
-int e2e_attention_loc_full(const float *key, const float *value, const float *query, const float *prev_att,
+int e2e_attention_loc_full(const float *key_t, const float *value, const float *query, const float *prev_att,
                            const int *enc_len, const float *w_conv, const float *w_proj, const float *w_energy,
                            float b_energy, float temperature, int n_run, int B, int T, int A, int K, int W, int E,
                            int hyps_per_cta, float *attn, float *ctx, void *stream);

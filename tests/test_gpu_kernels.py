@@ -317,7 +317,7 @@ def test_attention_loc_full_matches_oracle(cuda, n_utts, beam, t_len, dim, n_fil
     dev = lambda t: t.to(cuda)
     outs = []
     for nb in (0, 1, 2, 4):
-        got_a, got_c = ops.attention_loc_full(dev(key), dev(value), dev(query), dev(prev), dev(enc_len), dev(conv_w), dev(w_proj),
+        got_a, got_c = ops.attention_loc_full(dev(key).transpose(1, 2).contiguous(), dev(value), dev(query), dev(prev), dev(enc_len), dev(conv_w), dev(w_proj),
                                               dev(w_e), 0.25, 0.5, beam, hyps_per_cta=nb)
         outs.append((got_a.cpu(), got_c.cpu()))
     got_a, got_c = outs[0]
@@ -331,7 +331,7 @@ def test_attention_loc_full_matches_oracle(cuda, n_utts, beam, t_len, dim, n_fil
     if n_utts > 1:                                      # n_run: rows of later utterances stay untouched
         attn = torch.full((n, t_len), -7.0, device=cuda)
         ctx = torch.full((n, e_dim), -7.0, device=cuda)
-        ops.attention_loc_full(dev(key), dev(value), dev(query), dev(prev), dev(enc_len), dev(conv_w), dev(w_proj), dev(w_e),
+        ops.attention_loc_full(dev(key).transpose(1, 2).contiguous(), dev(value), dev(query), dev(prev), dev(enc_len), dev(conv_w), dev(w_proj), dev(w_e),
                                0.25, 0.5, beam, n_run=1, attn=attn, ctx=ctx)
         assert torch.equal(attn[:beam].cpu(), got_a[:beam]) and (attn[beam:] == -7.0).all() and (ctx[beam:] == -7.0).all()
 
