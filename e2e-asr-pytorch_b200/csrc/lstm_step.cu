@@ -64,7 +64,20 @@ struct CellParams {
     float *c_new, *h_new; __nv_bfloat16 *a_next; long long a_pitch; int K_next, off_next;
 };
 
-// one thread per (row, hidden unit); gate order i, f, g, o (torch.nn.LSTM)
+__device__ __forceinline__ void lstm_unit(const float (&g)[4], const float (&b)[4], const float *tb, float c, float &c2, float &h2)
+{
+    float z[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        z[q] = __fadd_rn(g[q], b[q]);                       // y + (b_ih + b_hh)
+        if (tb) z[q] = __fadd_rn(tb[q], z[q]);              // + layer-0 input projection
+    }
+    c2 = __fadd_rn(__fmul_rn(sigmoid_f32(z[1]), c), __fmul_rn(sigmoid_f32(z[0]), tanhf(z[2])));
+    h2 = __fmul_rn(sigmoid_f32(z[3]), tanhf(c2));
+}
+
+// one thread per (row, kW consecutive hidden units); gate order i, f, g, o (torch.nn.LSTM)
+template <int kW>
 __global__ void __launch_bounds__(256)
 lstm_cell_kernel(const CellParams p)
 {
@@ -73,22 +86,60 @@ lstm_cell_kernel(const CellParams p)
     const float *tb = p.table ? p.table + p.tok[r] * (long long)(4 * p.D) : nullptr;
     const long long prow = p.idx ? p.idx[r] : r;
     const float *cp = p.c_prev + prow * p.D;
-    for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < p.D; d += gridDim.x * blockDim.x) {
-        float z[4];
+    for (int d = (blockIdx.x * blockDim.x + threadIdx.x) * kW; d < p.D; d += gridDim.x * blockDim.x * kW) {
+        float gv[4][kW], bv[4][kW], tv[4][kW], cv[kW];
+        if (kW == 4) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            z[q] = __fadd_rn(__ldg(g + q * p.D + d), __ldg(p.bias + q * p.D + d));      // y + (b_ih + b_hh)
-            if (tb) z[q] = __fadd_rn(__ldg(tb + q * p.D + d), z[q]);                    // + layer-0 input projection
+            for (int q = 0; q < 4; ++q) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(g + q * p.D + d));
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + q * p.D + d));
+                gv[q][0] = a.x; gv[q][1] = a.y; gv[q][2] = a.z; gv[q][3] = a.w;
+                bv[q][0] = b.x; bv[q][1] = b.y; bv[q][2] = b.z; bv[q][3] = b.w;
+                if (tb) {
+                    const float4 t = __ldg(reinterpret_cast<const float4 *>(tb + q * p.D + d));
+                    tv[q][0] = t.x; tv[q][1] = t.y; tv[q][2] = t.z; tv[q][3] = t.w;
+                }
+            }
+            const float4 c = __ldg(reinterpret_cast<const float4 *>(cp + d));
+            cv[0] = c.x; cv[1] = c.y; cv[2] = c.z; cv[3] = c.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                gv[q][0] = __ldg(g + q * p.D + d);
+                bv[q][0] = __ldg(p.bias + q * p.D + d);
+                if (tb) tv[q][0] = __ldg(tb + q * p.D + d);
+            }
+            cv[0] = __ldg(cp + d);
         }
-        const float c2 = __fadd_rn(__fmul_rn(sigmoid_f32(z[1]), __ldg(cp + d)), __fmul_rn(sigmoid_f32(z[0]), tanhf(z[2])));
-        const float h2 = __fmul_rn(sigmoid_f32(z[3]), tanhf(c2));
-        p.c_new[(long long)r * p.D + d] = c2;
-        p.h_new[(long long)r * p.D + d] = h2;
+        float c2[kW], h2[kW];
+#pragma unroll
+        for (int i = 0; i < kW; ++i) {
+            const float gi[4] = {gv[0][i], gv[1][i], gv[2][i], gv[3][i]};
+            const float bi[4] = {bv[0][i], bv[1][i], bv[2][i], bv[3][i]};
+            const float ti[4] = {tb ? tv[0][i] : 0.0f, tb ? tv[1][i] : 0.0f, tb ? tv[2][i] : 0.0f, tb ? tv[3][i] : 0.0f};
+            lstm_unit(gi, bi, tb ? ti : nullptr, cv[i], c2[i], h2[i]);
+        }
+        float *co = p.c_new + (long long)r * p.D + d, *ho = p.h_new + (long long)r * p.D + d;
+        if (kW == 4) {
+            *reinterpret_cast<float4 *>(co) = make_float4(c2[0], c2[1], c2[2], c2[3]);
+            *reinterpret_cast<float4 *>(ho) = make_float4(h2[0], h2[1], h2[2], h2[3]);
+        } else {
+            co[0] = c2[0]; ho[0] = h2[0];
+        }
         if (p.a_next) {
-            __nv_bfloat16 a1, a2, a3;
-            split3(h2, a1, a2, a3);
             __nv_bfloat16 *o = p.a_next + (long long)r * p.a_pitch + p.off_next + d;
-            o[0] = a1; o[p.K_next] = a2; o[2 * p.K_next] = a3;
+            if (kW == 4) {
+                Bf16x4 p0, p1, p2;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split3(h2[i], p0.v[i], p1.v[i], p2.v[i]);
+                *reinterpret_cast<Bf16x4 *>(o) = p0;
+                *reinterpret_cast<Bf16x4 *>(o + p.K_next) = p1;
+                *reinterpret_cast<Bf16x4 *>(o + 2 * p.K_next) = p2;
+            } else {
+                __nv_bfloat16 a1, a2, a3;
+                split3(h2[0], a1, a2, a3);
+                o[0] = a1; o[p.K_next] = a2; o[2 * p.K_next] = a3;
+            }
         }
     }
 }
@@ -140,7 +191,14 @@ extern "C" int e2e_lstm_cell(const float *gates, long long gates_pitch, const fl
     p.gates = gates; p.gates_pitch = gates_pitch; p.bias = bias; p.table = table; p.tok = tok;
     p.c_prev = c_prev; p.idx = row_idx; p.D = D; p.a_pitch = a_pitch; p.K_next = K_next; p.off_next = off_next;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int bx = (D + 255) / 256;
+    const bool vec = (D % 4 == 0) && (gates_pitch % 4 == 0) && !(reinterpret_cast<uintptr_t>(gates) & 15) &&
+                     !(reinterpret_cast<uintptr_t>(bias) & 15) && !(reinterpret_cast<uintptr_t>(table) & 15) &&
+                     !(reinterpret_cast<uintptr_t>(c_prev) & 15) && !(reinterpret_cast<uintptr_t>(c_new) & 15) &&
+                     !(reinterpret_cast<uintptr_t>(h_new) & 15) &&
+                     (!a_next_bf16 || ((a_pitch % 4 == 0) && (K_next % 4 == 0) && (off_next % 4 == 0) && !(reinterpret_cast<uintptr_t>(a_next_bf16) & 7)));
+    const int per_thread = vec ? 4 : 1;
+    const int threads = D / per_thread >= 256 ? 256 : ((D / per_thread + 31) / 32 * 32);
+    const int bx = (D + threads * per_thread - 1) / (threads * per_thread);
     for (int r0 = 0; r0 < n; r0 += 65535) {
         const int rows = n - r0 < 65535 ? n - r0 : 65535;
         p.n = rows;
@@ -151,7 +209,8 @@ extern "C" int e2e_lstm_cell(const float *gates, long long gates_pitch, const fl
         p.c_new = c_new + (long long)r0 * D;
         p.h_new = h_new + (long long)r0 * D;
         p.a_next = a_next_bf16 ? static_cast<__nv_bfloat16 *>(a_next_bf16) + (long long)r0 * a_pitch : nullptr;
-        lstm_cell_kernel<<<dim3(bx, rows), 256, 0, st>>>(p);
+        if (vec) lstm_cell_kernel<4><<<dim3(bx, rows), threads, 0, st>>>(p);
+        else lstm_cell_kernel<1><<<dim3(bx, rows), threads, 0, st>>>(p);
         count_launch();
     }
     return check_launch("e2e_lstm_cell");

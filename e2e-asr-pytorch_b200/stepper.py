@@ -165,6 +165,7 @@ class _FusedLstm:
         self.h = [[torch.zeros(n, d, device=device) for _ in range(self.layers)] for _ in range(2)]
         self.c = [[torch.zeros(n, d, device=device) for _ in range(self.layers)] for _ in range(2)]
         self.a = [torch.empty(n, 3 * (self.k_in[l] + d), dtype=torch.bfloat16, device=device) for l in range(self.layers)]
+        self.gates = torch.empty(n, 4 * d, device=device)          # GEMM accumulator, reused by every layer
         self.idx = torch.arange(n, device=device)
         self.cur = 0
 
@@ -185,9 +186,10 @@ class _FusedLstm:
         for l in range(self.layers):
             k = self.k_in[l] + d
             a, lin = self.a[l][:n], self.lin[l]
-            y = torch.mm(a, lin.b2, out_dtype=torch.float32)
-            y = torch.addmm(y, a[:, :2 * k], lin.b1, out_dtype=torch.float32)
-            y = torch.addmm(y, a[:, :k], lin.b0, out_dtype=torch.float32)
+            y = self.gates[:n]                                         # accumulate in place: no C-operand copies
+            torch.mm(a, lin.b2, out_dtype=torch.float32, out=y)
+            torch.addmm(y, a[:, :2 * k], lin.b1, out_dtype=torch.float32, out=y)
+            torch.addmm(y, a[:, :k], lin.b0, out_dtype=torch.float32, out=y)
             nxt = l + 1 < self.layers
             ops.lstm_cell(y, self.bias[l], self.c[cur][l], idx, n, self.c[new][l], self.h[new][l],
                           table=self.table0 if l == 0 else None, tok=tok if (l == 0 and self.table0 is not None) else None,
