@@ -271,9 +271,11 @@ def _cpu_worker(job):
     return time.time() - t0, (1 + (steps - 1) * BEAM) * int(1.5 * BEAM) * frames, len(nb)
 
 
-def cpu_sample_jobs(n_jobs, frames=240):
-    """Bounded sample: ``n_jobs`` utterances of ``frames`` input frames each (short on purpose — a
-    median 6.4 s utterance costs ~1 CPU-minute; utts/s therefore FLATTERS the CPU)."""
+def cpu_sample_jobs(n_jobs, frames=640):
+    """Bounded sample: ``n_jobs`` utterances of ``frames`` input frames each.  The default is the
+    workload's MEDIAN length (6.4 s); one such utterance costs ~25 s of one core, and the cost grows
+    ~quadratically with the length (decode steps x encoder frames), so against the workload's mean
+    cost (equivalent to ~840 frames) utts/s on this sample still flatters the CPU by ~1.7x."""
     return [(100000 + k, frames) for k in range(n_jobs)]
 
 
@@ -294,8 +296,8 @@ def cpu_baseline(args, sample_utts=None):
     with ctx.Pool(procs) as pool:
         wall, units = cpu_pass(pool, jobs)
     return {"value": n_jobs / wall, "unit": "utts/s", "cores": procs, "kind": "port",
-            "sample": "%d synthetic utts of %d input frames (%.1f s audio) each, one per process, oracle/beam_oracle.py "
-                      "(numpy prefix score + PyTorch-CPU modules), %.1f s wall" % (n_jobs, args.cpu_frames, args.cpu_frames / 100.0, wall),
+            "sample": "%d synthetic utts of %d input frames (%.1f s audio, the workload's median length) each, one per process, "
+                      "oracle/beam_oracle.py (numpy prefix score + PyTorch-CPU modules), %.1f s wall" % (n_jobs, args.cpu_frames, args.cpu_frames / 100.0, wall),
             "cand_frames_per_s": units / wall}
 
 
@@ -309,8 +311,8 @@ def run_reference(args):
     jobs = cpu_sample_jobs(args.cpu_sample or procs, args.cpu_frames)
     ctx = mp.get_context("fork")
     with ctx.Pool(procs) as pool:
-        for _ in range(args.warmup):
-            cpu_pass(pool, jobs[:procs])
+        for _ in range(args.warmup):          # builds the models in every worker; short utterances keep it cheap
+            cpu_pass(pool, cpu_sample_jobs(procs, 80))
         t0 = time.time()
         units = 0
         for _ in range(args.steps):
@@ -318,8 +320,9 @@ def run_reference(args):
             units += u
         wall = time.time() - t0
     value = len(jobs) * args.steps / wall
-    sample = "%d synthetic utts of %d input frames per step, one per process, oracle port of the reference " \
-             "(reference is Python under /root/reference and cannot travel)" % (len(jobs), args.cpu_frames)
+    sample = "%d synthetic utts of %d input frames (the workload's median length; CPU cost grows ~L^2, the workload's " \
+             "mean-cost-equivalent length is ~840 frames) per step, one per process, oracle port of the reference " \
+             "(the reference is Python under /root/reference and cannot travel to the GPU box)" % (len(jobs), args.cpu_frames)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "utts/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
@@ -345,7 +348,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0)
-    ap.add_argument("--cpu-frames", type=int, default=240)
+    ap.add_argument("--cpu-frames", type=int, default=640, help="length of the CPU sample's utterances (640 = workload median)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

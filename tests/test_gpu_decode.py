@@ -192,3 +192,25 @@ def test_decode_batch_is_order_independent(cuda):
     for k, n in enumerate(lens):
         alone = dec(feat[k:k + 1, :n].to(cuda), fl[k:k + 1].to(cuda))
         assert [h.outIndex for h in alone] == [h.outIndex for h in both[k]], k
+
+
+def test_decode_dataset_feeds_the_reference_result_files(cuda, tmp_path):
+    """f-3: decode_dataset + write_results reproduce the reference's per-utterance flow (bin/test_asr.py:138-156):
+    same tuples as one-utterance-per-call decoding, files in the reference's layout, scorable by results.score_file."""
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth, results as R
+    from tests.test_results import CharTok
+    asr = synth.build_asr(31, synth.TINY_ASR_CFG, seed=0, peak=4.0)
+    dec = BeamDecoder(asr, None, 4, 0.01, 0.2, ctc_weight=0.5).to(cuda)
+    lens = [64, 92, 40, 76, 92]
+    rng = np.random.default_rng(0)
+    samples = [("utt%d" % i, synth.utterance(i, n), [int(t) for t in rng.integers(3, 31, 8)] + [1]) for i, n in enumerate(lens)]
+    res = R.decode_dataset(dec, samples, cuda, max_utts=3)              # forces two batches
+    assert [r[0] for r in res] == [s[0] for s in samples]
+    for (name, hyps, truth), (_, feat, tr) in zip(res, samples):
+        one = dec(feat[None].to(cuda), torch.LongTensor([feat.shape[0]]).to(cuda))      # the reference's call shape
+        assert hyps == [h.outIndex for h in one] and truth == tr
+    best, beam = str(tmp_path / "dev_output.csv"), str(tmp_path / "dev_beam.csv")
+    R.init_result_files(best, beam)
+    R.write_results(res, CharTok(), best, beam)
+    assert R.score_file(best)["utterances"] == len(lens)
+    assert R.score_file(beam, beam=True)["rows"] == sum(len(r[1]) for r in res)
