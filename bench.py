@@ -35,6 +35,16 @@ N_UTTS = 2620
 METRIC = "beam-8+LM joint CTC/attn decode utts/sec"
 
 
+def load_traffic():
+    """DRAM bytes per prefix-score launch, averaged over the launches of one timed pass of this same
+    command under ncu (profiles/r01_prefix_traffic_inbench.json; tools/summarize_ncu.py made it)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_prefix_traffic_inbench.json")))
+        return float(d["dram_bytes_per_launch"]), "profiles/r01_prefix_traffic_inbench.json (ncu dram__bytes_read+write, mean of 660 launches)"
+    except Exception:
+        return None, None
+
+
 def load_peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -204,6 +214,9 @@ def run_b200(args):
     k_total_ms = float(sum(k_ms))
     bytes_per_unit = 12.0 + 12.0 / dec.ctc_beam_size
     peak, peak_src = load_peaks()
+    traffic, traffic_src = load_traffic()
+    if args.n_utts != N_UTTS:
+        traffic, traffic_src = None, None          # the capture is of the full workload
     achieved = units_formula * bytes_per_unit / (k_total_ms * 1e-3) / 1e9 if k_total_ms > 0 else 0.0
     achieved_rows = units_rows * bytes_per_unit / (k_total_ms * 1e-3) / 1e9 if k_total_ms > 0 else 0.0
     dec.profile_prefix = False
@@ -229,7 +242,9 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "prefix_score_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": units_formula * bytes_per_unit / max(1, len(ev)),
+                     "peak_source": peak_src,
                      "bytes_per_cand_frame": bytes_per_unit, "cand_frames_per_step": stats_units,
                      "kernel_ms_per_step": k_total_ms / max(1, args.steps), "launches_per_step": len(ev) / max(1, args.steps),
                      "kernel_share_of_step": k_total_ms / ms,

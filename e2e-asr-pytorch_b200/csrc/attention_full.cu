@@ -4,28 +4,33 @@
 //     energy = gen_energy(tanh(key + query + loc))                src/module.py:1168
 //     attn   = softmax(mask(energy / temperature))                src/module.py:1109-1113
 //     ctx    = attn x value                                       src/module.py:1114
-// for every live hypothesis n = u*B + b of the first n_run utterances.  Nothing of shape
+// for every hypothesis n = u*B + b of the first n_run utterances.  Nothing of shape
 // [U*B, T, *] is ever materialised: per step the kernel reads key/value of each utterance,
 // the previous alignments and the queries, and writes the new alignments and contexts.
 //
-// Mapping: one CTA per (utterance, group of NB beam slots), one THREAD per encoder frame t
-// (256 frames per pass) that carries the NB hypotheses of the group together, so a key value is
-// fetched once per group (the keys arrive channel-major, key_t[u][a][t], so the warp's 32 frames
-// are one coalesced 128-byte load per channel) and the per-channel constants (loc_proj row, gen_energy weight, the
-// NB queries) are shared-memory broadcasts.  Frames t >= enc_len[u] are never touched: a batch
-// padded to the longest utterance costs nothing.  tanh(x) = 1 - 2/(1 + exp(2x)) through
-// MUFU.EX2 + MUFU.RCP (absolute error ~2e-7); the kernel is MUFU-bound by construction
-// (4 MUFU per (hypothesis, frame, channel)).
-// The context product runs in the same CTA afterwards: thread <-> 4 output columns (16-byte
-// loads, 4 frames in flight), the NB alignments are read as one broadcast LDS.128 per frame.
-// Results do not depend on NB (every hypothesis sees the same operations in the same order),
-// so the host picks NB by launch size only.
+// Mapping: one CTA (8 warps) per utterance, all B beam slots.
+//   phase 1 (energies): the work is cut into warp-sized units (32 consecutive frames) x (NB beam
+//     slots) that the warps take round robin, so a 113-frame and an 825-frame utterance keep their
+//     lanes equally busy; lane <-> frame.  A unit stages the +-P frame window of its NB previous
+//     alignments in warp-private shared memory, runs the K-filter convolution into registers and
+//     then walks the A channels: the key arrives channel-major (key_t[u][a][t]: one coalesced
+//     128-byte load per channel per warp), the per-channel constants (loc_proj row, gen_energy
+//     weight, the B queries) are shared-memory broadcasts.  tanh(x) = 1 - 2/(1 + exp(2x)) through
+//     MUFU.EX2 + MUFU.RCP (absolute error ~2e-7); 4 MUFU per (hypothesis, frame, channel) make
+//     this phase MUFU/issue bound by construction.  Frames t >= enc_len[u] are never touched.
+//     Energies are parked in the output alignment rows (global, L2 resident).
+//   phase 2 (masked softmax): one warp per beam slot, in place on the alignment rows.
+//   phase 3 (context): thread <-> 4 output columns, ALL B alignments against one pass over the
+//     utterance's value rows (16-byte coalesced loads, 4 frames in flight).
+// Results do not depend on NB (every hypothesis sees the same operations in the same order).
 #include "common.cuh"
 
 namespace e2e {
 
 constexpr int kAfThreads = 256;
+constexpr int kAfWarps = kAfThreads / 32;
 constexpr int kAfMaxK = 12;
+constexpr int kAfMaxB = 32;
 
 __device__ __forceinline__ float af_tanh(float x)
 {
@@ -38,61 +43,63 @@ __device__ __forceinline__ float af_tanh(float x)
 struct AttFullParams {
     const float *key_t, *value, *query, *prev_att; const int *enc_len;
     const float *w_conv, *w_proj, *w_energy; float b_energy, temperature;
-    int B, T, A, K, W, E, groups;
+    int B, T, A, K, W, E;
     float *attn, *ctx;
 };
 
-// shared memory (floats): pa [NB][TP] | wc [W][KP] | cst [A][20] | es [T4][NB] | red [8*NB]
+// shared memory (floats): wc [W][KP] | cst [A][16] (loc_proj row 0..11, gen_energy weight at 12) |
+//                         q [A][Bq] | pa [warps][NB][32 + W - 1]
 template <int NB, int KP>
-__global__ void __launch_bounds__(kAfThreads)
+__global__ void __launch_bounds__(kAfThreads, 3)
 attention_full_kernel(const AttFullParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int u = blockIdx.x / p.groups, g = blockIdx.x - u * p.groups;
-    const int T = p.T, A = p.A, K = p.K, W = p.W, P = W / 2;
+    const int u = blockIdx.x;
+    const int T = p.T, A = p.A, K = p.K, W = p.W, P = W / 2, B = p.B;
     const int Tu = min(p.enc_len[u], T);
-    const int b0 = g * NB;                                    // first beam slot of this group
-    const int TP = (T + W - 1 + 3) & ~3;
-    const int T4 = (T + 3) & ~3;
-    float *pa = reinterpret_cast<float *>(smem_raw);
-    float *wc = pa + NB * TP;
+    const int Bq = (B + 3) & ~3;                               // query row pitch
+    const int win = 32 + W - 1;                                // frames a unit's convolution reads per hypothesis
+    float *wc = reinterpret_cast<float *>(smem_raw);
     float4 *cst = reinterpret_cast<float4 *>(wc + ((W * KP + 3) & ~3));
-    float *es = reinterpret_cast<float *>(cst + (size_t)A * 5);
-    float *red = es + (size_t)T4 * NB;
+    float *qs = reinterpret_cast<float *>(cst + (size_t)A * 4);
+    float *pa = qs + (size_t)A * Bq + (size_t)warp * NB * win;
+    float *arow = p.attn + (size_t)u * B * T;                  // this utterance's alignment rows [B][T]
 
-    // ---- stage: previous alignments with a zero halo, filters, per-channel constants ----------
-    for (int i = tid; i < NB * TP; i += kAfThreads) {
-        const int b = i / TP, tt = i - b * TP - P;
-        float v = 0.0f;
-        if (b0 + b < p.B && tt >= 0 && tt < Tu) v = __ldg(p.prev_att + ((size_t)u * p.B + b0 + b) * T + tt);
-        pa[i] = v;
-    }
+    // ---- stage: filters, per-channel constants, queries ----------------------------------------------
     for (int i = tid; i < W * KP; i += kAfThreads) {
         const int j = i / KP, k = i - j * KP;
         wc[i] = (k < K) ? __ldg(p.w_conv + (size_t)k * W + j) : 0.0f;
     }
     for (int a = tid; a < A; a += kAfThreads) {
-        float w[kAfMaxK];
+        float w[16];
 #pragma unroll
-        for (int k = 0; k < kAfMaxK; ++k) w[k] = (k < K) ? __ldg(p.w_proj + (size_t)a * K + k) : 0.0f;
-        float q[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int k = 0; k < 16; ++k) w[k] = 0.0f;
 #pragma unroll
-        for (int b = 0; b < NB; ++b)
-            if (b0 + b < p.B) q[b] = __ldg(p.query + ((size_t)u * p.B + b0 + b) * A + a);
-        cst[a * 5 + 0] = make_float4(w[0], w[1], w[2], w[3]);
-        cst[a * 5 + 1] = make_float4(w[4], w[5], w[6], w[7]);
-        cst[a * 5 + 2] = make_float4(w[8], w[9], w[10], w[11]);
-        cst[a * 5 + 3] = make_float4(q[0], q[1], q[2], q[3]);
-        cst[a * 5 + 4] = make_float4(__ldg(p.w_energy + a), 0.0f, 0.0f, 0.0f);
+        for (int k = 0; k < kAfMaxK; ++k)
+            if (k < K) w[k] = __ldg(p.w_proj + (size_t)a * K + k);
+        w[12] = __ldg(p.w_energy + a);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cst[a * 4 + q] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    }
+    for (int i = tid; i < A * Bq; i += kAfThreads) {
+        const int a = i / Bq, b = i - a * Bq;
+        qs[i] = (b < B) ? __ldg(p.query + ((size_t)u * B + b) * A + a) : 0.0f;
     }
     __syncthreads();
 
-    // ---- energies ---------------------------------------------------------------------------------
-    for (int t = tid; t < T; t += kAfThreads) {
-        float s[NB];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) s[b] = -INFINITY;
+    // ---- phase 1: energies, warp-sized units (frame tile, NB beam slots) -----------------------------
+    const int n_tiles = (Tu + 31) / 32, n_groups = (B + NB - 1) / NB;
+    for (int unit = warp; unit < n_tiles * n_groups; unit += kAfWarps) {
+        const int tile = unit / n_groups, g = unit - tile * n_groups;
+        const int t0 = tile * 32, b0 = g * NB;
+        const int t = t0 + lane;
+        __syncwarp();                                          // previous unit's window is no longer read
+        for (int i = lane; i < NB * win; i += 32) {
+            const int b = i / win, tt = t0 - P + (i - b * win);
+            pa[i] = (b0 + b < B && tt >= 0 && tt < Tu) ? __ldg(p.prev_att + ((size_t)u * B + b0 + b) * T + tt) : 0.0f;
+        }
+        __syncwarp();
         if (t < Tu) {
             // location features: f[b][k] = sum_j w_conv[k][j] * prev_att[b][t + j - P]
             float f[NB][KP];
@@ -100,7 +107,7 @@ attention_full_kernel(const AttFullParams p)
             for (int b = 0; b < NB; ++b)
 #pragma unroll
                 for (int k = 0; k < KP; ++k) f[b][k] = 0.0f;
-            const float *pat = pa + t;
+            const float *pat = pa + lane;
 #pragma unroll 2
             for (int j = 0; j < W; ++j) {
                 float wj[KP];
@@ -111,7 +118,7 @@ attention_full_kernel(const AttFullParams p)
                 }
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
-                    const float a = pat[b * TP + j];
+                    const float a = pat[b * win + j];
 #pragma unroll
                     for (int k = 0; k < KP; ++k) f[b][k] = fmaf(wj[k], a, f[b][k]);
                 }
@@ -126,11 +133,20 @@ attention_full_kernel(const AttFullParams p)
                 for (int i = 0; i < 4; ++i) kk[i] = __ldg(kcol + (size_t)(a4 * 4 + i) * T);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 *c = cst + (a4 * 4 + i) * 5;
-                    const float4 c0 = c[0], c1 = c[1], c2 = c[2], cq = c[3];
-                    const float we = c[4].x;
+                    const int a = a4 * 4 + i;
+                    const float4 c0 = cst[a * 4], c1 = cst[a * 4 + 1], c2 = cst[a * 4 + 2], c3 = cst[a * 4 + 3];
                     const float wp[kAfMaxK] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
-                    const float qq[4] = {cq.x, cq.y, cq.z, cq.w};
+                    const float we = c3.x;
+                    float qq[NB];
+                    if (NB == 4) {
+                        const float4 q4 = *reinterpret_cast<const float4 *>(qs + a * Bq + b0);
+                        qq[0] = q4.x; qq[1 % NB] = q4.y; qq[2 % NB] = q4.z; qq[3 % NB] = q4.w;
+                    } else if (NB == 2) {
+                        const float2 q2 = *reinterpret_cast<const float2 *>(qs + a * Bq + b0);
+                        qq[0] = q2.x; qq[1 % NB] = q2.y;
+                    } else {
+                        qq[0] = qs[a * Bq + b0];
+                    }
 #pragma unroll
                     for (int b = 0; b < NB; ++b) {
                         float loc = wp[0] * f[b][0];
@@ -142,106 +158,110 @@ attention_full_kernel(const AttFullParams p)
                 }
             }
 #pragma unroll
-            for (int b = 0; b < NB; ++b) s[b] = __fdiv_rn(acc[b], p.temperature);
+            for (int b = 0; b < NB; ++b)
+                if (b0 + b < B) arow[(size_t)(b0 + b) * T + t] = __fdiv_rn(acc[b], p.temperature);
         }
-#pragma unroll
-        for (int b = 0; b < NB; ++b) es[t * NB + b] = s[b];
     }
-    __syncthreads();
+    __syncthreads();      // (also orders the global energy writes before the reads below: same CTA)
 
-    // ---- masked softmax over t, one hypothesis after the other (module.py:1109-1113) ---------------
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
+    // ---- phase 2: masked softmax over t, one warp per beam slot (module.py:1109-1113) -----------------
+    for (int b = warp; b < B; b += kAfWarps) {
+        float *row = arow + (size_t)b * T;
         float m = -INFINITY;
-        for (int t = tid; t < T; t += kAfThreads) m = fmaxf(m, es[t * NB + b]);
+        for (int t = lane; t < Tu; t += 32) m = fmaxf(m, row[t]);
         m = warp_max(m);
-        if (lane == 0) red[warp] = m;
-        __syncthreads();
-        m = red[0];
-        for (int w = 1; w < kAfThreads / 32; ++w) m = fmaxf(m, red[w]);
-        __syncthreads();
         float sum = 0.0f;
-        for (int t = tid; t < T; t += kAfThreads) {
-            const float e = (t < Tu) ? expf(es[t * NB + b] - m) : 0.0f;
-            es[t * NB + b] = e;
+        for (int t = lane; t < Tu; t += 32) {
+            const float e = expf(row[t] - m);
+            row[t] = e;
             sum += e;
         }
         sum = warp_sum(sum);
-        if (lane == 0) red[warp] = sum;
-        __syncthreads();
-        sum = 0.0f;
-        for (int w = 0; w < kAfThreads / 32; ++w) sum += red[w];
-        const bool real = b0 + b < p.B;
-        float *out = p.attn + ((size_t)u * p.B + b0 + b) * T;
-        for (int t = tid; t < T; t += kAfThreads) {
-            const float a = __fdiv_rn(es[t * NB + b], sum);
-            es[t * NB + b] = a;
-            if (real) out[t] = a;
-        }
-        __syncthreads();
+        for (int t = lane; t < T; t += 32) row[t] = (t < Tu) ? __fdiv_rn(row[t], sum) : 0.0f;
     }
+    __syncthreads();
 
-    // ---- context: ctx[b][e] = sum_t attn[b][t] * value[u][t][e]  (module.py:1114) -------------------
-    // thread <-> 4 consecutive columns (one 16-byte load per frame, whole row coalesced), 4 frames in flight
+    // ---- phase 3: ctx[b][e] = sum_t attn[b][t] * value[u][t][e]  (module.py:1114) ----------------------
+    // thread <-> 4 consecutive columns (one 16-byte load per frame, whole row coalesced), 4 frames in flight;
+    // beam slots in chunks of 8 accumulators per column
     const float *vbase = p.value + (size_t)u * T * p.E;
-    if ((p.E & 3) == 0) {
-        for (int e = tid * 4; e < p.E; e += kAfThreads * 4) {
-            float acc[NB][4];
+    constexpr int kBC = 8;
+    const bool t_vec = (T & 3) == 0;
+    for (int bc = 0; bc < B; bc += kBC) {
+        const int nb = min(kBC, B - bc);
+        const float *ar = arow + (size_t)bc * T;
+        if ((p.E & 3) == 0) {
+            for (int e = tid * 4; e < p.E; e += kAfThreads * 4) {
+                float acc[kBC][4];
 #pragma unroll
-            for (int b = 0; b < NB; ++b)
+                for (int b = 0; b < kBC; ++b)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[b][i] = 0.0f;
-            const float *vp = vbase + e;
-            int t = 0;
-            for (; t + 4 <= Tu; t += 4) {
-                float4 v[4];
+                    for (int i = 0; i < 4; ++i) acc[b][i] = 0.0f;
+                const float *vp = vbase + e;
+                int t = 0;
+                for (; t + 4 <= Tu; t += 4) {
+                    float4 v[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const float4 *>(vp + (size_t)(t + q) * p.E));
+                    for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const float4 *>(vp + (size_t)(t + q) * p.E));
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
+                    for (int b = 0; b < kBC; ++b) {
+                        if (b < nb) {
+                            float a[4];
+                            if (t_vec) {                                     // broadcast load (L1), 16 bytes when rows are aligned
+                                const float4 a4 = *reinterpret_cast<const float4 *>(ar + (size_t)b * T + t);
+                                a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
+                            } else {
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) {
-                        const float a = es[(t + q) * NB + b];
-                        acc[b][0] = fmaf(a, v[q].x, acc[b][0]); acc[b][1] = fmaf(a, v[q].y, acc[b][1]);
-                        acc[b][2] = fmaf(a, v[q].z, acc[b][2]); acc[b][3] = fmaf(a, v[q].w, acc[b][3]);
+                                for (int q = 0; q < 4; ++q) a[q] = ar[(size_t)b * T + t + q];
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                acc[b][0] = fmaf(a[q], v[q].x, acc[b][0]); acc[b][1] = fmaf(a[q], v[q].y, acc[b][1]);
+                                acc[b][2] = fmaf(a[q], v[q].z, acc[b][2]); acc[b][3] = fmaf(a[q], v[q].w, acc[b][3]);
+                            }
+                        }
                     }
-            }
-            for (; t < Tu; ++t) {
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(vp + (size_t)t * p.E));
-#pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    const float a = es[t * NB + b];
-                    acc[b][0] = fmaf(a, v.x, acc[b][0]); acc[b][1] = fmaf(a, v.y, acc[b][1]);
-                    acc[b][2] = fmaf(a, v.z, acc[b][2]); acc[b][3] = fmaf(a, v.w, acc[b][3]);
                 }
+                for (; t < Tu; ++t) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(vp + (size_t)t * p.E));
+#pragma unroll
+                    for (int b = 0; b < kBC; ++b) {
+                        if (b < nb) {
+                            const float a = ar[(size_t)b * T + t];
+                            acc[b][0] = fmaf(a, v.x, acc[b][0]); acc[b][1] = fmaf(a, v.y, acc[b][1]);
+                            acc[b][2] = fmaf(a, v.z, acc[b][2]); acc[b][3] = fmaf(a, v.w, acc[b][3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < kBC; ++b)
+                    if (b < nb)
+                        *reinterpret_cast<float4 *>(p.ctx + ((size_t)u * B + bc + b) * p.E + e) = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
             }
+        } else {
+            for (int e = tid; e < p.E; e += kAfThreads) {
+                float acc[kBC];
 #pragma unroll
-            for (int b = 0; b < NB; ++b)
-                if (b0 + b < p.B)
-                    *reinterpret_cast<float4 *>(p.ctx + ((size_t)u * p.B + b0 + b) * p.E + e) = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
-        }
-    } else {
-        for (int e = tid; e < p.E; e += kAfThreads) {
-            float acc[NB];
+                for (int b = 0; b < kBC; ++b) acc[b] = 0.0f;
+                const float *vp = vbase + e;
+                for (int t = 0; t < Tu; ++t) {
+                    const float v = __ldg(vp + (size_t)t * p.E);
 #pragma unroll
-            for (int b = 0; b < NB; ++b) acc[b] = 0.0f;
-            const float *vp = vbase + e;
-            for (int t = 0; t < Tu; ++t) {
-                const float v = __ldg(vp + (size_t)t * p.E);
+                    for (int b = 0; b < kBC; ++b)
+                        if (b < nb) acc[b] = fmaf(ar[(size_t)b * T + t], v, acc[b]);
+                }
 #pragma unroll
-                for (int b = 0; b < NB; ++b) acc[b] = fmaf(es[t * NB + b], v, acc[b]);
+                for (int b = 0; b < kBC; ++b)
+                    if (b < nb) p.ctx[((size_t)u * B + bc + b) * p.E + e] = acc[b];
             }
-#pragma unroll
-            for (int b = 0; b < NB; ++b)
-                if (b0 + b < p.B) p.ctx[((size_t)u * p.B + b0 + b) * p.E + e] = acc[b];
         }
     }
 }
 
-static size_t att_full_smem(int NB, int KP, int T, int A, int W)
+static size_t att_full_smem(int NB, int KP, int A, int W, int B)
 {
-    const size_t TP = (size_t)((T + W - 1 + 3) & ~3), T4 = (size_t)((T + 3) & ~3);
-    return ((size_t)NB * TP + (size_t)((W * KP + 3) & ~3) + (size_t)A * 20 + T4 * NB + 8 * NB + 8) * 4;
+    const size_t Bq = (size_t)((B + 3) & ~3);
+    return ((size_t)((W * KP + 3) & ~3) + (size_t)A * 16 + (size_t)A * Bq + (size_t)kAfWarps * NB * (32 + W - 1) + 8) * 4;
 }
 
 template <int NB>
@@ -254,13 +274,13 @@ static int att_full_launch(const AttFullParams &p, int KP, int n_run, cudaStream
         case 10: kern = attention_full_kernel<NB, 10>; break;
         default: kern = attention_full_kernel<NB, 12>; break;
     }
-    const size_t smem = att_full_smem(NB, KP, p.T, p.A, p.W);
+    const size_t smem = att_full_smem(NB, KP, p.A, p.W, p.B);
     if (smem > 200 * 1024) return set_error(E2E_ERR_UNSUPPORTED, "e2e_attention_loc_full: %zu bytes of shared memory needed", smem);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(E2E_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    kern<<<(unsigned)(n_run * p.groups), kAfThreads, smem, st>>>(p);
+    kern<<<(unsigned)n_run, kAfThreads, smem, st>>>(p);
     count_launch();
     return check_launch("e2e_attention_loc_full");
 }
@@ -270,27 +290,24 @@ static int att_full_launch(const AttFullParams &p, int KP, int n_run, cudaStream
 extern "C" int e2e_attention_loc_full(const float *key_t, const float *value, const float *query, const float *prev_att,
                                       const int *enc_len, const float *w_conv, const float *w_proj, const float *w_energy,
                                       float b_energy, float temperature, int n_run, int B, int T, int A, int K, int W, int E,
-                                      int hyps_per_cta, float *attn, float *ctx, void *stream)
+                                      int hyps_per_unit, float *attn, float *ctx, void *stream)
 {
     using namespace e2e;
     if (!key_t || !value || !query || !prev_att || !enc_len || !w_conv || !w_proj || !w_energy || !attn || !ctx)
         return set_error(E2E_ERR_ARG, "e2e_attention_loc_full: null pointer");
     if (n_run <= 0 || B <= 0 || T <= 0 || A <= 0 || K <= 0 || W <= 0 || E <= 0) return set_error(E2E_ERR_ARG, "e2e_attention_loc_full: bad size");
-    if (K > kAfMaxK || (A & 3) != 0 || (W & 1) == 0)
-        return set_error(E2E_ERR_UNSUPPORTED, "e2e_attention_loc_full: needs loc_kernel_num <= 12, dim %% 4 == 0 and an odd filter length");
-    if ((reinterpret_cast<uintptr_t>(value) & 15) || (reinterpret_cast<uintptr_t>(ctx) & 15))
-        return set_error(E2E_ERR_ARG, "e2e_attention_loc_full: value and ctx must be 16-byte aligned");
-    int NB = hyps_per_cta;
-    if (NB <= 0) {   // by launch size: enough CTAs to cover the machine, otherwise as much key reuse as possible
-        const long long want = 2LL * 148;
-        NB = ((long long)n_run * ((B + 3) / 4) >= want || B == 1) ? 4 : (((long long)n_run * ((B + 1) / 2) >= want) ? 2 : 1);
-    }
-    if (NB != 1 && NB != 2 && NB != 4) return set_error(E2E_ERR_ARG, "e2e_attention_loc_full: hyps_per_cta must be 0, 1, 2 or 4");
+    if (K > kAfMaxK || (A & 3) != 0 || (W & 1) == 0 || B > kAfMaxB)
+        return set_error(E2E_ERR_UNSUPPORTED, "e2e_attention_loc_full: needs loc_kernel_num <= 12, dim %% 4 == 0, an odd filter length and beam <= 32");
+    if ((reinterpret_cast<uintptr_t>(value) & 15) || (reinterpret_cast<uintptr_t>(ctx) & 15) || (reinterpret_cast<uintptr_t>(attn) & 15))
+        return set_error(E2E_ERR_ARG, "e2e_attention_loc_full: value, attn and ctx must be 16-byte aligned");
+    int NB = hyps_per_unit;
+    if (NB <= 0) NB = 2;
+    if (NB != 1 && NB != 2 && NB != 4) return set_error(E2E_ERR_ARG, "e2e_attention_loc_full: hyps_per_unit must be 0, 1, 2 or 4");
     while (NB > 1 && NB / 2 >= B) NB /= 2;
     AttFullParams p;
     p.key_t = key_t; p.value = value; p.query = query; p.prev_att = prev_att; p.enc_len = enc_len;
     p.w_conv = w_conv; p.w_proj = w_proj; p.w_energy = w_energy; p.b_energy = b_energy; p.temperature = temperature;
-    p.B = B; p.T = T; p.A = A; p.K = K; p.W = W; p.E = E; p.groups = (B + NB - 1) / NB;
+    p.B = B; p.T = T; p.A = A; p.K = K; p.W = W; p.E = E;
     p.attn = attn; p.ctx = ctx;
     const int KP = K <= 4 ? 4 : (K <= 8 ? 8 : (K <= 10 ? 10 : 12));
     cudaStream_t st = static_cast<cudaStream_t>(stream);

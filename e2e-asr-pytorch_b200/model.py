@@ -113,6 +113,65 @@ class VGGFrontEnd(nn.Module):
         return out.view(out.shape[0], out.shape[1], self.out_dim), feat_len // 4
 
 
+    # -- fp32-accurate tensor-core path (CUDA only; SURVEY §8f row f-4) ---------------------------------
+    A_BYTES = 3 << 30      # budget of the unfolded bf16 operand per GEMM block
+
+    def _split_weights(self, conv):
+        """[9*Cin, Cout] GEMM weights of a 3x3 convolution as the three bf16 operand stacks of
+        stepper.SplitLinear (k = (dy*3+dx)*Cin + c), cached per layer and device."""
+        from .stepper import SplitLinear
+        cache = self.__dict__.setdefault("_split_cache", {})
+        key = (id(conv), conv.weight.device)
+        if key not in cache:
+            w2d = conv.weight.detach().permute(2, 3, 1, 0).reshape(-1, conv.out_channels).t().contiguous()   # [Cout, 9*Cin]
+            cache[key] = SplitLinear(w2d)
+        return cache[key]
+
+    def _conv_split(self, x, valid, conv):
+        """x [N,H,W,C] fp32 NHWC, valid [N] int32 -> relu(conv(x) + b) [N,H,W,Cout] NHWC, rows >= valid zeroed."""
+        from . import ops
+        n, h, w, c = x.shape
+        k = 9 * c
+        lin = self._split_weights(conv)
+        total = n * h * w
+        blk = max(1, min(total, self.A_BYTES // (3 * k * 2)))
+        a = torch.empty((blk, 3 * k), dtype=torch.bfloat16, device=x.device)
+        y = torch.empty((total, conv.out_channels), dtype=torch.float32, device=x.device)
+        for p0 in range(0, total, blk):
+            m = min(blk, total - p0)
+            ops.conv3x3_unfold_split(x, valid, p0, m, a)
+            am, ym = a[:m], y[p0:p0 + m]
+            torch.mm(am, lin.b2, out_dtype=torch.float32, out=ym)                      # a1w3 + a2w2 + a3w1
+            torch.addmm(ym, am[:, :2 * k], lin.b1, out_dtype=torch.float32, out=ym)    # + a1w2 + a2w1
+            torch.addmm(ym, am[:, :k], lin.b0, out_dtype=torch.float32, out=ym)        # + a1w1
+        y = y.view(n, h, w, conv.out_channels)
+        ops.conv_bias_relu_mask(y, conv.bias.detach().float().contiguous(), valid)
+        return y
+
+    def forward_masked_split(self, feat, feat_len):
+        """forward_masked with the three wide convolutions (128->128, 128->256, 256->256: 98 % of the
+        front end's FLOPs) on the tensor cores: activations stay NHWC, each layer is unfold+split
+        (csrc/conv_split.cu) -> three bf16 GEMMs with fp32 accumulation -> bias/ReLU/mask kernel.  The
+        4->128 layer (K = 36) and the pooling stay library calls."""
+        img = self._as_image(feat)
+        n, _, t, _ = img.shape
+        own = (feat_len // 4 * 4).to(img.device)
+        v1 = own.to(torch.int32).contiguous()
+        v2 = (own // 2).to(torch.int32).contiguous()
+        convs = [m for m in self.extractor if isinstance(m, nn.Conv2d)]
+        mask = (torch.arange(t, device=img.device)[None, :] < own[:, None])[:, None, :, None].to(img.dtype)
+        x = (img * mask).contiguous(memory_format=torch.channels_last)
+        y = F.relu(F.conv2d(x, convs[0].weight, convs[0].bias, padding=1))             # cuDNN, channels_last
+        y = y.permute(0, 2, 3, 1).contiguous()                                         # NHWC (a view when cuDNN kept channels_last)
+        y = self._conv_split(y, v1, convs[1])                                          # rows >= own read as zero inside
+        y = F.max_pool2d(y.permute(0, 3, 1, 2), 2, stride=2, ceil_mode=True).permute(0, 2, 3, 1).contiguous()
+        y = self._conv_split(y, v2, convs[2])
+        y = self._conv_split(y, v2, convs[3])
+        y = F.max_pool2d(y.permute(0, 3, 1, 2), 2, stride=2, ceil_mode=True)           # [N, C2, T/4, F/4]
+        out = y.permute(0, 2, 1, 3).contiguous()                                       # [N, T/4, C2, F/4]
+        return out.view(out.shape[0], out.shape[1], self.out_dim), feat_len // 4
+
+
 class RecurrentLayer(nn.Module):
     """(B)LSTM/GRU + optional LayerNorm/dropout/sub-sampling/projection (module.py:1003-1081)."""
 
@@ -219,7 +278,10 @@ class Encoder(nn.Module):
         batch-1 calls: masked VGG + per-row reversed recurrent layers."""
         for layer in self.layers:
             if isinstance(layer, VGGFrontEnd):
-                x, x_len = layer.forward_masked(x, x_len)
+                if getattr(self, "split_conv", False) and x.is_cuda:
+                    x, x_len = layer.forward_masked_split(x, x_len)
+                else:
+                    x, x_len = layer.forward_masked(x, x_len)
             else:
                 x, x_len = layer.forward_ragged(x, x_len)
         return x, x_len

@@ -177,7 +177,7 @@ def attention_loc_step(key, query, loc_feat, enc_len, w_proj, w_energy, b_energy
 
 
 def attention_loc_full(key_t, value, query, prev_att, enc_len, w_conv, w_proj, w_energy, b_energy, temperature, beam,
-                       n_run=None, hyps_per_cta=0, attn=None, ctx=None):
+                       n_run=None, hyps_per_unit=0, attn=None, ctx=None):
     """The whole location-aware attention step (conv + energies + masked softmax + context) for the first
     ``n_run`` utterances: key_t [U,A,T] (channel-major keys), value [U,T,E], query [>=n_run*B,A],
     prev_att [>=n_run*B,T], w_conv [K,W] -> (attn [n_run*B,T], ctx [n_run*B,E])."""
@@ -202,7 +202,7 @@ def attention_loc_full(key_t, value, query, prev_att, enc_len, w_conv, w_proj, w
     _chk(ctx, F32, "ctx", n * e)
     L.check(L.load().e2e_attention_loc_full(L.ptr(key_t), L.ptr(value), L.ptr(query), L.ptr(prev_att), L.ptr(enc_len),
                                            L.ptr(w_conv), L.ptr(w_proj), L.ptr(w_energy), float(b_energy), float(temperature),
-                                           n_run, int(beam), int(t_len), int(a), int(k), int(w), int(e), int(hyps_per_cta),
+                                           n_run, int(beam), int(t_len), int(a), int(k), int(w), int(e), int(hyps_per_unit),
                                            L.ptr(attn), L.ptr(ctx), _stream()))
     return attn, ctx
 
@@ -238,6 +238,25 @@ def lstm_cell(gates, bias, c_prev, row_idx, n, c_new, h_new, table=None, tok=Non
     L.check(L.load().e2e_lstm_cell(L.ptr(gates), int(gates.stride(0)), L.ptr(bias), L.ptr(table), L.ptr(tok), L.ptr(c_prev),
                                   L.ptr(row_idx), int(n), int(d), L.ptr(c_new), L.ptr(h_new), L.ptr(a_next),
                                   int(a_next.stride(0)) if a_next is not None else 0, int(k_next), int(off_next), _stream()))
+
+
+def conv3x3_unfold_split(x_nhwc, valid_rows, first_pixel, n_pixels, out):
+    """Unfold + 3-piece bf16 split of a block of NHWC pixels (see e2e_conv3x3_unfold_split): out [>=n_pixels, 27*C]."""
+    _chk(x_nhwc, F32, "x_nhwc")
+    _chk(valid_rows, I32, "valid_rows", x_nhwc.shape[0])
+    _chk(out, torch.bfloat16, "out", n_pixels * 27 * x_nhwc.shape[3])
+    n, h, w, c = x_nhwc.shape
+    L.check(L.load().e2e_conv3x3_unfold_split(L.ptr(x_nhwc), L.ptr(valid_rows), n, h, w, c, int(first_pixel), int(n_pixels),
+                                             L.ptr(out), _stream()))
+
+
+def conv_bias_relu_mask(y_nhwc, bias, valid_rows):
+    """In place: y = relu(y + bias) on rows h < valid_rows[n], 0 elsewhere; y [N,H,W,C] NHWC."""
+    _chk(y_nhwc, F32, "y_nhwc")
+    _chk(bias, F32, "bias", y_nhwc.shape[3])
+    _chk(valid_rows, I32, "valid_rows", y_nhwc.shape[0])
+    n, h, w, c = y_nhwc.shape
+    L.check(L.load().e2e_conv_bias_relu_mask(L.ptr(y_nhwc), L.ptr(bias), L.ptr(valid_rows), n, h, w, c, 0, n * h * w, _stream()))
 
 
 def launch_count():

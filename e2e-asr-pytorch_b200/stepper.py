@@ -209,6 +209,7 @@ class BatchedStepper:
         if att.mode not in ("loc", "dot"):
             raise NotImplementedError("attention mode " + str(att.mode))
         self.asr, self.lm = asr, lm
+        self.split_conv = bool(split_gemm)       # VGG convolutions as fp32-accurate bf16 tensor-core GEMMs (model.py)
         self.mode, self.temperature = att.mode, att.att_layer.temperature
         # fused device LSTM steps (csrc/lstm_step.cu) whenever the weights live on a GPU; the plain
         # PyTorch cells otherwise (CPU tests of the host logic, GRU models)
@@ -240,6 +241,7 @@ class BatchedStepper:
         if n_utts == 1:
             enc, enc_len = enc_mod(feats, lens)
         elif hasattr(enc_mod, "forward_ragged"):
+            enc_mod.split_conv = self.split_conv and feats.is_cuda
             lens_host = lens.cpu()
             outs, ls = [], []
             for lo in range(0, n_utts, chunk):
@@ -266,6 +268,10 @@ class BatchedStepper:
             enc_len = torch.stack(ls)
         enc_len = enc_len.to(enc.device).long().clamp(max=enc.shape[1])
         t_max = int(enc_len.max())
+        if n_utts > 1:
+            t_max = (t_max + 3) // 4 * 4          # 16-byte aligned alignment rows for the attention kernel; the extra frames are masked
+        if t_max > enc.shape[1]:
+            enc = torch.nn.functional.pad(enc, (0, 0, 0, t_max - enc.shape[1]))
         return enc[:, :t_max].contiguous(), enc_len
 
     def start(self, enc, enc_len, beam):

@@ -186,12 +186,12 @@ int e2e_attention_loc_step(const float *key, const float *query, const float *lo
  *   key_t [U][A][T] (the keys tanh(proj_k(enc)), src/asr.py:343, stored CHANNEL-major), value [U][T][E],
  *   query [n][A], prev_att [n][T] (zero beyond enc_len[u]),
  *   w_conv [K][W], w_proj [A][K], w_energy [A]; attn [n][T], ctx [n][E].
- *   hyps_per_cta: 0 (choose by launch size) or 1, 2, 4 — the result does not depend on it.
- *   Needs K <= 12, A % 4 == 0, W odd. */
+ *   hyps_per_unit: beam slots a warp carries together, 0 (default) or 1, 2, 4 — the result does not depend on it.
+ *   Needs K <= 12, A % 4 == 0, W odd, B <= 32; fastest when T % 4 == 0 and E % 4 == 0. */
 int e2e_attention_loc_full(const float *key_t, const float *value, const float *query, const float *prev_att,
                            const int *enc_len, const float *w_conv, const float *w_proj, const float *w_energy,
                            float b_energy, float temperature, int n_run, int B, int T, int A, int K, int W, int E,
-                           int hyps_per_cta, float *attn, float *ctx, void *stream);
+                           int hyps_per_unit, float *attn, float *ctx, void *stream);
 
 /* (next) One-token LSTM step of the batched RNNLM (src/lm.py:27-38: nn.LSTM on a
  * [1,1] token) and speller (src/asr.py:259-266).  The recurrent GEMMs stay library calls on an exact 3-piece
@@ -216,6 +216,21 @@ int e2e_lstm_cell(const float *gates, long long gates_pitch, const float *bias, 
                   const float *c_prev, const long long *row_idx, int n, int D,
                   float *c_new, float *h_new, void *a_next_bf16, long long a_pitch, int K_next, int off_next,
                   void *stream);
+
+/* (next) 3x3 "same" convolutions of the VGG front end (src/module.py:672-686) as
+ * fp32-accurate tensor-core GEMMs: unfold a block of NHWC pixels into the GEMM's A operand as the exact
+ * 3-piece bf16 split [a1 | a2 | a3] of every fp32 value,
+ *   out[p - first_pixel][piece*9C + (dy*3+dx)*C + c] = piece(in[n][h+dy-1][w+dx-1][c])   (zero outside the image
+ *   and for source rows h+dy-1 >= valid_rows[n]: the masking a padded batch row needs to equal a batch-1 call),
+ * p = (n*H + h)*W + w.  The GEMM against weight.permute(2,3,1,0).reshape(9C, Cout) is a library call.
+ *   in_nhwc fp32 [N][H][W][C], C % 4 == 0; out bf16 [n_pixels][27*C]. */
+int e2e_conv3x3_unfold_split(const float *in_nhwc, const int *valid_rows, int N, int H, int W, int C,
+                             long long first_pixel, int n_pixels, void *out_bf16, void *stream);
+
+/* In place on the GEMM result (NHWC): y = relu(y + bias) on rows h < valid_rows[n], 0 elsewhere
+ * (Conv2d bias + nn.ReLU of src/module.py:672-686 + the inter-layer masking). */
+int e2e_conv_bias_relu_mask(float *y_nhwc, const float *bias, const int *valid_rows, int N, int H, int W, int C,
+                            long long first_pixel, long long n_pixels, void *stream);
 
 /* Number of kernel launches issued through this library by the calling process
  * (for bench.py's gpu_launches claim). */

@@ -214,3 +214,23 @@ def test_decode_dataset_feeds_the_reference_result_files(cuda, tmp_path):
     R.write_results(res, CharTok(), best, beam)
     assert R.score_file(best)["utterances"] == len(lens)
     assert R.score_file(beam, beam=True)["rows"] == sum(len(r[1]) for r in res)
+
+
+@pytest.mark.parametrize("vocab,beam,lm_w,lens,max_ratio", [(300, 8, 0.5, [64, 120, 92], 0.07),      # cfg3-like: Vp > 256 -> column-gather prefix kernel
+                                                             (31, 16, 0.3, [240, 200, 96], 0.2)])     # cfg4-like: beam 16 (C = 24, 384 lanes per utterance)
+def test_decode_large_vocab_and_wide_beam_match_oracle(cuda, vocab, beam, lm_w, lens, max_ratio):
+    """End-to-end decode vs the per-hypothesis CPU oracle on the two shapes the bench does not run: a vocabulary
+    wide enough for the gather variant of kernel (2) (with the subword config's max_len_ratio) and beam 16."""
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth
+    asr, lm, lm_path, lm_cfg = _models(vocab=vocab)
+    feat, fl = synth.padded_batch(list(range(len(lens))), lens)
+    dec = BeamDecoder(asr, None, beam, 0.01, max_ratio, lm_path=lm_path, lm_config=lm_cfg, lm_weight=lm_w, ctc_weight=0.5).to(cuda)
+    out = dec.decode_batch(feat.to(cuda), fl.to(cuda))
+    same = ties = 0
+    for k, n in enumerate(lens):
+        ora = _oracle_nbest(asr, lm, feat[k], n, beam, lm_w, 0.5, max_ratio=max_ratio)
+        assert len(out[k]) == len(ora)
+        s, t = _compare(out[k], ora, "V %d beam %d utt %d" % (vocab, beam, k))
+        same, ties = same + s, ties + t
+    print("V %d beam %d: identical 1-best %d/%d, ties %d" % (vocab, beam, same, len(lens), ties))
+    assert same >= len(lens) - 1

@@ -318,7 +318,7 @@ def test_attention_loc_full_matches_oracle(cuda, n_utts, beam, t_len, dim, n_fil
     outs = []
     for nb in (0, 1, 2, 4):
         got_a, got_c = ops.attention_loc_full(dev(key).transpose(1, 2).contiguous(), dev(value), dev(query), dev(prev), dev(enc_len), dev(conv_w), dev(w_proj),
-                                              dev(w_e), 0.25, 0.5, beam, hyps_per_cta=nb)
+                                              dev(w_e), 0.25, 0.5, beam, hyps_per_unit=nb)
         outs.append((got_a.cpu(), got_c.cpu()))
     got_a, got_c = outs[0]
     err_a, err_c = (got_a - want_a).abs().max().item(), (got_c - want_c).abs().max().item()
@@ -422,3 +422,60 @@ def test_fused_lstm_stack_matches_nn_lstm(cuda):
                 fused.reorder(perm.to(cuda))
                 h, c = h[:, perm], c[:, perm]
                 assert (fused.hidden(n).cpu().double() - torch.cat(list(h), dim=1)).abs().max().item() < 2e-6
+
+
+# ----------------------------------------------------------------------------------------------
+# f-4: VGG convolutions as split-bf16 tensor-core GEMMs
+# ----------------------------------------------------------------------------------------------
+def test_conv_unfold_split_matches_unfold(cuda):
+    """The unfolded operand equals torch's unfold of the masked NHWC input, piece by piece (bit exact)."""
+    ops, _ = _ops()
+    from e2e_asr_pytorch_b200.stepper import _split3
+    g = torch.Generator().manual_seed(0)
+    n, h, w, c = 3, 9, 5, 8
+    x = torch.randn(n, h, w, c, generator=g)
+    valid = torch.tensor([9, 4, 6], dtype=torch.int32)
+    xm = x.clone()
+    for i in range(n):
+        xm[i, int(valid[i]):] = 0
+    cols = torch.nn.functional.unfold(xm.permute(0, 3, 1, 2), 3, padding=1)          # [N, C*9, H*W], k = c*9 + tap
+    want = cols.view(n, c, 9, h * w).permute(0, 3, 2, 1).reshape(n * h * w, 9 * c)      # k = tap*C + c
+    k = 9 * c
+    for p0, m in [(0, n * h * w), (7, 50)]:
+        out = torch.zeros(m, 3 * k, dtype=torch.bfloat16, device=cuda)
+        ops.conv3x3_unfold_split(x.to(cuda), valid.to(cuda), p0, m, out)
+        pieces = _split3(want[p0:p0 + m].to(cuda))
+        for q in range(3):
+            assert torch.equal(out[:, q * k:(q + 1) * k], pieces[q])
+
+
+def test_vgg_split_conv_path_is_fp32_accurate(cuda):
+    """VGGFrontEnd.forward_masked_split (NHWC + unfold/split + bf16 GEMMs + bias/ReLU/mask kernel) against a float64
+    evaluation of forward_masked: not less accurate than the cuDNN fp32 path, padded rows exactly zero."""
+    _ops()
+    from e2e_asr_pytorch_b200.model import VGGFrontEnd, reference_init_
+    from e2e_asr_pytorch_b200.decode import _Fp32Math
+    torch.manual_seed(0)
+    vgg = VGGFrontEnd(160)
+    vgg.apply(reference_init_)
+    for m in vgg.extractor:
+        if isinstance(m, torch.nn.Conv2d):
+            m.bias.data.normal_(0, 0.1)
+    vgg.eval()
+    lens = torch.tensor([96, 40, 68])
+    feat = torch.randn(3, 96, 160)
+    for i, l in enumerate(lens):
+        feat[i, int(l):] = 0
+    with torch.no_grad():
+        want, wl = VGGFrontEnd.forward_masked(vgg.double(), feat.double(), lens)
+        vgg.float().to(cuda)
+        with _Fp32Math():
+            got, gl = vgg.forward_masked_split(feat.to(cuda), lens.to(cuda))
+            ref32, _ = vgg.forward_masked(feat.to(cuda), lens.to(cuda))
+    assert torch.equal(gl.cpu(), wl)
+    err_split = (got.cpu().double() - want).abs().max().item()
+    err_cudnn = (ref32.cpu().double() - want).abs().max().item()
+    print("vgg split conv: max |split - fp64| = %.3g, max |cudnn fp32 - fp64| = %.3g, scale %.3g" % (err_split, err_cudnn, want.abs().max().item()))
+    assert err_split < max(2 * err_cudnn, 2e-6 * want.abs().max().item())
+    for i, l in enumerate(lens):
+        assert (got[i, int(l) // 4:] == 0).all()

@@ -44,7 +44,7 @@ def main():
     ctx = torch.empty(n, E, device=dev)
     key_t = key.transpose(1, 2).contiguous()
     run = lambda: ops.attention_loc_full(key_t, value, query, prev, enc_len, w_conv, w_proj, w_e, 0.1, 0.5, B,
-                                         hyps_per_cta=a.nb, attn=attn, ctx=ctx)
+                                         hyps_per_unit=a.nb, attn=attn, ctx=ctx)
     for _ in range(3):
         run()
     torch.cuda.synchronize()
