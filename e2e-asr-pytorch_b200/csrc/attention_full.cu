@@ -8,8 +8,9 @@
 // [U*B, T, *] is ever materialised: per step the kernel reads key/value of each utterance,
 // the previous alignments and the queries, and writes the new alignments and contexts.
 //
-// Mapping: one CTA (8 warps) per utterance, all B beam slots.
-//   phase 1 (energies): the work is cut into warp-sized units (32 consecutive frames) x (NB beam
+// Two launches, both sized by the work and not by the batch: few long utterances (the tail of a
+// decode) are spread over many CTAs, many utterances get one CTA each.
+//   kernel A (energies): CTA <-> (utterance, share of its units); the work is cut into warp-sized units (32 consecutive frames) x (NB beam
 //     slots) that the warps take round robin, so a 113-frame and an 825-frame utterance keep their
 //     lanes equally busy; lane <-> frame.  A unit stages the +-P frame window of its NB previous
 //     alignments in warp-private shared memory, runs the K-filter convolution into registers and
@@ -19,9 +20,10 @@
 //     MUFU.EX2 + MUFU.RCP (absolute error ~2e-7); 4 MUFU per (hypothesis, frame, channel) make
 //     this phase MUFU/issue bound by construction.  Frames t >= enc_len[u] are never touched.
 //     Energies are parked in the output alignment rows (global, L2 resident).
-//   phase 2 (masked softmax): one warp per beam slot, in place on the alignment rows.
-//   phase 3 (context): thread <-> 4 output columns, ALL B alignments against one pass over the
-//     utterance's value rows (16-byte coalesced loads, 4 frames in flight).
+//   kernel B, CTA <-> (utterance, group of beam slots):
+//     masked softmax, one warp per beam slot, in place on the alignment rows; then the context:
+//     thread <-> 4 output columns, the group's alignments against one pass over the utterance's
+//     value rows (16-byte coalesced loads, 4 frames in flight).
 // Results do not depend on NB (every hypothesis sees the same operations in the same order).
 #include "common.cuh"
 
@@ -44,6 +46,8 @@ struct AttFullParams {
     const float *key_t, *value, *query, *prev_att; const int *enc_len;
     const float *w_conv, *w_proj, *w_energy; float b_energy, temperature;
     int B, T, A, K, W, E;
+    int unit_ctas;      // kernel A: CTAs per utterance (they share its units round robin)
+    int slot_ctas;      // kernel B: CTAs per utterance; each takes ceil(B / slot_ctas) beam slots
     float *attn, *ctx;
 };
 
@@ -51,11 +55,11 @@ struct AttFullParams {
 //                         q [A][Bq] | pa [warps][NB][32 + W - 1]
 template <int NB, int KP>
 __global__ void __launch_bounds__(kAfThreads, 3)
-attention_full_kernel(const AttFullParams p)
+attention_energy_kernel(const AttFullParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int u = blockIdx.x;
+    const int u = blockIdx.x / p.unit_ctas, part = blockIdx.x - u * p.unit_ctas;
     const int T = p.T, A = p.A, K = p.K, W = p.W, P = W / 2, B = p.B;
     const int Tu = min(p.enc_len[u], T);
     const int Bq = (B + 3) & ~3;                               // query row pitch
@@ -88,9 +92,9 @@ attention_full_kernel(const AttFullParams p)
     }
     __syncthreads();
 
-    // ---- phase 1: energies, warp-sized units (frame tile, NB beam slots) -----------------------------
+    // ---- energies, warp-sized units (frame tile, NB beam slots) ---------------------------------------
     const int n_tiles = (Tu + 31) / 32, n_groups = (B + NB - 1) / NB;
-    for (int unit = warp; unit < n_tiles * n_groups; unit += kAfWarps) {
+    for (int unit = part + warp * p.unit_ctas; unit < n_tiles * n_groups; unit += kAfWarps * p.unit_ctas) {
         const int tile = unit / n_groups, g = unit - tile * n_groups;
         const int t0 = tile * 32, b0 = g * NB;
         const int t = t0 + lane;
@@ -162,10 +166,22 @@ attention_full_kernel(const AttFullParams p)
                 if (b0 + b < B) arow[(size_t)(b0 + b) * T + t] = __fdiv_rn(acc[b], p.temperature);
         }
     }
-    __syncthreads();      // (also orders the global energy writes before the reads below: same CTA)
+}
 
-    // ---- phase 2: masked softmax over t, one warp per beam slot (module.py:1109-1113) -----------------
-    for (int b = warp; b < B; b += kAfWarps) {
+// kernel B: masked softmax + context for beam slots [b_lo, b_hi) of one utterance
+__global__ void __launch_bounds__(kAfThreads)
+attention_softmax_context_kernel(const AttFullParams p)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int u = blockIdx.x / p.slot_ctas, part = blockIdx.x - u * p.slot_ctas;
+    const int T = p.T, B = p.B;
+    const int Tu = min(p.enc_len[u], T);
+    const int per = (B + p.slot_ctas - 1) / p.slot_ctas;
+    const int b_lo = part * per, b_hi = min(B, b_lo + per);
+    float *arow = p.attn + (size_t)u * B * T;                  // this utterance's alignment rows [B][T]
+
+    // ---- masked softmax over t, one warp per beam slot (module.py:1109-1113) --------------------------
+    for (int b = b_lo + warp; b < b_hi; b += kAfWarps) {
         float *row = arow + (size_t)b * T;
         float m = -INFINITY;
         for (int t = lane; t < Tu; t += 32) m = fmaxf(m, row[t]);
@@ -181,14 +197,14 @@ attention_full_kernel(const AttFullParams p)
     }
     __syncthreads();
 
-    // ---- phase 3: ctx[b][e] = sum_t attn[b][t] * value[u][t][e]  (module.py:1114) ----------------------
+    // ---- ctx[b][e] = sum_t attn[b][t] * value[u][t][e]  (module.py:1114) -------------------------------
     // thread <-> 4 consecutive columns (one 16-byte load per frame, whole row coalesced), 4 frames in flight;
     // beam slots in chunks of 8 accumulators per column
     const float *vbase = p.value + (size_t)u * T * p.E;
     constexpr int kBC = 8;
     const bool t_vec = (T & 3) == 0;
-    for (int bc = 0; bc < B; bc += kBC) {
-        const int nb = min(kBC, B - bc);
+    for (int bc = b_lo; bc < b_hi; bc += kBC) {
+        const int nb = min(kBC, b_hi - bc);
         const float *ar = arow + (size_t)bc * T;
         if ((p.E & 3) == 0) {
             for (int e = tid * 4; e < p.E; e += kAfThreads * 4) {
@@ -265,14 +281,14 @@ static size_t att_full_smem(int NB, int KP, int A, int W, int B)
 }
 
 template <int NB>
-static int att_full_launch(const AttFullParams &p, int KP, int n_run, cudaStream_t st)
+static int att_full_launch(AttFullParams &p, int KP, int n_run, cudaStream_t st)
 {
     void (*kern)(AttFullParams) = nullptr;
     switch (KP) {
-        case 4: kern = attention_full_kernel<NB, 4>; break;
-        case 8: kern = attention_full_kernel<NB, 8>; break;
-        case 10: kern = attention_full_kernel<NB, 10>; break;
-        default: kern = attention_full_kernel<NB, 12>; break;
+        case 4: kern = attention_energy_kernel<NB, 4>; break;
+        case 8: kern = attention_energy_kernel<NB, 8>; break;
+        case 10: kern = attention_energy_kernel<NB, 10>; break;
+        default: kern = attention_energy_kernel<NB, 12>; break;
     }
     const size_t smem = att_full_smem(NB, KP, p.A, p.W, p.B);
     if (smem > 200 * 1024) return set_error(E2E_ERR_UNSUPPORTED, "e2e_attention_loc_full: %zu bytes of shared memory needed", smem);
@@ -280,8 +296,19 @@ static int att_full_launch(const AttFullParams &p, int KP, int n_run, cudaStream
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(E2E_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    kern<<<(unsigned)n_run, kAfThreads, smem, st>>>(p);
-    count_launch();
+    // Enough CTAs to cover the machine a few times over whatever the number of utterances: an utterance's
+    // units (kernel A) and beam slots (kernel B) are shared out over more CTAs when few utterances are live.
+    const int want = 3 * 148;
+    const int max_units = ((p.T + 31) / 32) * ((p.B + NB - 1) / NB);
+    int ua = (want + n_run - 1) / n_run;
+    ua = ua < 1 ? 1 : (ua > (max_units + kAfWarps - 1) / kAfWarps ? (max_units + kAfWarps - 1) / kAfWarps : ua);
+    int ub = (want + n_run - 1) / n_run;
+    ub = ub < 1 ? 1 : (ub > p.B ? p.B : ub);
+    p.unit_ctas = ua;
+    p.slot_ctas = ub;
+    kern<<<(unsigned)(n_run * ua), kAfThreads, smem, st>>>(p);
+    attention_softmax_context_kernel<<<(unsigned)(n_run * ub), kAfThreads, 0, st>>>(p);
+    count_launch(2);
     return check_launch("e2e_attention_loc_full");
 }
 
