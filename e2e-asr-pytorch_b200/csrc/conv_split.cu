@@ -31,33 +31,45 @@ __global__ void __launch_bounds__(256)
 im2col3x3_split_kernel(const float *__restrict__ in, const int *__restrict__ valid, int H, int W, int C,
                        long long p0, int P, __nv_bfloat16 *__restrict__ out)
 {
+    // one warp per output pixel (its coordinates are decoded once, warp uniform); the lanes sweep the
+    // pixel's 9 taps x C/4 channel groups: 512-byte contiguous reads, 256-byte contiguous writes per piece
     const int C4 = C >> 2;
-    const int per_pixel = 9 * C4;                              // float4 groups per output row
     const long long K = 9LL * C;
-    const long long total = (long long)P * per_pixel;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int pl = (int)(i / per_pixel);
-        const int r = (int)(i - (long long)pl * per_pixel);
-        const int tap = r / C4, c4 = r - tap * C4;
-        const int dy = tap / 3, dx = tap - dy * 3;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+    for (int pl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pl < P; pl += warps_per_grid) {
         const long long p = p0 + pl;
         const int w = (int)(p % W);
         const long long nh = p / W;
         const int h = (int)(nh % H);
         const int n = (int)(nh / H);
-        const int hs = h + dy - 1, ws = w + dx - 1;
-        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (hs >= 0 && hs < H && ws >= 0 && ws < W && hs < __ldg(valid + n))
-            v = __ldg(reinterpret_cast<const float4 *>(in + (((long long)n * H + hs) * W + ws) * C) + c4);
-        ConvBf16x4 q0, q1, q2;
-        conv_split3(v.x, q0.v[0], q1.v[0], q2.v[0]);
-        conv_split3(v.y, q0.v[1], q1.v[1], q2.v[1]);
-        conv_split3(v.z, q0.v[2], q1.v[2], q2.v[2]);
-        conv_split3(v.w, q0.v[3], q1.v[3], q2.v[3]);
-        __nv_bfloat16 *o = out + (long long)pl * 3 * K + (long long)tap * C + c4 * 4;
-        *reinterpret_cast<ConvBf16x4 *>(o) = q0;
-        *reinterpret_cast<ConvBf16x4 *>(o + K) = q1;
-        *reinterpret_cast<ConvBf16x4 *>(o + 2 * K) = q2;
+        const int vrows = __ldg(valid + n);
+        const float *img = in + (long long)n * H * W * C;
+        __nv_bfloat16 *orow = out + (long long)pl * 3 * K;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int hs = h + dy - 1;
+            const bool row_ok = hs >= 0 && hs < H && hs < vrows;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int ws = w + dx - 1;
+                const bool ok = row_ok && ws >= 0 && ws < W;
+                const float4 *src = reinterpret_cast<const float4 *>(img + ((long long)hs * W + ws) * C);
+                __nv_bfloat16 *o = orow + (dy * 3 + dx) * C;
+                for (int c4 = lane; c4 < C4; c4 += 32) {
+                    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (ok) v = __ldg(src + c4);
+                    ConvBf16x4 q0, q1, q2;
+                    conv_split3(v.x, q0.v[0], q1.v[0], q2.v[0]);
+                    conv_split3(v.y, q0.v[1], q1.v[1], q2.v[1]);
+                    conv_split3(v.z, q0.v[2], q1.v[2], q2.v[2]);
+                    conv_split3(v.w, q0.v[3], q1.v[3], q2.v[3]);
+                    *reinterpret_cast<ConvBf16x4 *>(o + c4 * 4) = q0;
+                    *reinterpret_cast<ConvBf16x4 *>(o + K + c4 * 4) = q1;
+                    *reinterpret_cast<ConvBf16x4 *>(o + 2 * K + c4 * 4) = q2;
+                }
+            }
+        }
     }
 }
 
@@ -99,9 +111,8 @@ extern "C" int e2e_conv3x3_unfold_split(const float *in_nhwc, const int *valid_r
         return set_error(E2E_ERR_ARG, "e2e_conv3x3_unfold_split: bad size (C must be a multiple of 4)");
     if ((reinterpret_cast<uintptr_t>(in_nhwc) & 15) || (reinterpret_cast<uintptr_t>(out_bf16) & 7))
         return set_error(E2E_ERR_ARG, "e2e_conv3x3_unfold_split: misaligned buffer");
-    const long long total = (long long)n_pixels * 9 * (C / 4);
-    long long blocks = (total + 255) / 256;
-    if (blocks > 148LL * 32) blocks = 148LL * 32;             // grid-stride: a few waves of the machine
+    long long blocks = ((long long)n_pixels + 7) / 8;           // 8 warps per block, one pixel per warp at a time
+    if (blocks > 148LL * 64) blocks = 148LL * 64;             // grid-stride: a few waves of the machine
     im2col3x3_split_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         in_nhwc, valid_rows, H, W, C, first_pixel, n_pixels, static_cast<__nv_bfloat16 *>(out_bf16));
     count_launch();
