@@ -225,6 +225,10 @@ def run_b200(args):
     stats_units = units_formula / max(1, args.steps)
 
     if rank != 0:
+        # every rank leaves through the same barrier as rank 0 (a rank that returned early left rank 0 waiting
+        # in its last barrier until the NCCL watchdog aborted it)
+        dist.barrier()
+        dist.destroy_process_group()
         return
     ok = int((full[:, 0] >= 0).sum()) == n_total
     line = {
@@ -254,9 +258,10 @@ def run_b200(args):
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args, sample_utts=args.cpu_sample)
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------
