@@ -58,6 +58,27 @@ def reference_init_(module):
             raise NotImplementedError
 
 
+def split_gemm_rows(x, lin, a_bytes=3 << 30):
+    """y = x @ W^T (no bias) as fp32-accurate bf16 tensor-core GEMMs: x [F, K] fp32 (contiguous, CUDA),
+    ``lin`` a stepper.SplitLinear holding the weight's three operand stacks.  The exact 3-piece split of a
+    block of rows is written by one hand-written kernel (csrc/lstm_step.cu), the three GEMMs accumulate in
+    place; row blocks bound the size of the bf16 operand."""
+    from . import ops
+    f, k = x.shape
+    m_out = lin.b0.shape[1]
+    y = torch.empty((f, m_out), dtype=torch.float32, device=x.device)
+    blk = max(1, min(f, a_bytes // (3 * k * 2)))
+    a = torch.empty((blk, 3 * k), dtype=torch.bfloat16, device=x.device)
+    for r0 in range(0, f, blk):
+        m = min(blk, f - r0)
+        ops.lstm_split_rows(x[r0:r0 + m], None, m, a, k, 0)
+        am, ym = a[:m], y[r0:r0 + m]
+        torch.mm(am, lin.b2, out_dtype=torch.float32, out=ym)
+        torch.addmm(ym, am[:, :2 * k], lin.b1, out_dtype=torch.float32, out=ym)
+        torch.addmm(ym, am[:, :k], lin.b0, out_dtype=torch.float32, out=ym)
+    return y
+
+
 class VGGFrontEnd(nn.Module):
     """2x(conv3x3,conv3x3,maxpool2) front end, 4x time reduction (module.py:659-716)."""
 
@@ -241,6 +262,44 @@ class RecurrentLayer(nn.Module):
         return self._post(torch.cat([fw, bw], dim=-1), x_len)
 
 
+    # -- packed device path (CUDA only) ----------------------------------------------
+    def packed_supported(self):
+        rnn = self.layer
+        return (isinstance(rnn, nn.LSTM) and rnn.num_layers == 1 and self.sample_rate == 1 and not self.layer_norm
+                and rnn.hidden_size <= 384)
+
+    def _packed_weights(self):
+        from .stepper import SplitLinear
+        rnn = self.layer
+        cache = self.__dict__.setdefault("_packed_cache", {})
+        key = rnn.weight_hh_l0.device
+        if key not in cache:
+            sfx = ["", "_reverse"] if rnn.bidirectional else [""]
+            g = lambda n: getattr(rnn, n).detach().float()
+            w_in = torch.cat([g("weight_ih_l0" + x) for x in sfx], dim=0)                       # [dirs*4H, in]
+            dirs = [((g("bias_ih_l0" + x) + g("bias_hh_l0" + x)).contiguous(),
+                     g("weight_hh_l0" + x).t().contiguous()) for x in sfx]                         # w_t [H(k), 4H] == [H][4][H]
+            pj = (SplitLinear(self.pj.weight.detach().float()), self.pj.bias.detach().float()) if self.proj else None
+            cache[key] = (SplitLinear(w_in), dirs, pj)
+        return cache[key]
+
+    def forward_packed(self, x, frame_off, lens32, group_first, group_rows):
+        """x [F, in]: the valid frames of all utterances back to back (utterance n at rows frame_off[n] ..
+        + lens32[n]).  Input projections of both directions are one split-bf16 GEMM over all frames, the
+        recurrence is one persistent kernel launch (csrc/lstm_seq.cu), the projection another GEMM."""
+        from . import ops
+        lin_in, dirs, pj = self._packed_weights()
+        h = self.layer.hidden_size
+        gates = split_gemm_rows(x.contiguous(), lin_in)                                          # [F, dirs*4H]
+        out = torch.empty((x.shape[0], h * len(dirs)), dtype=torch.float32, device=x.device)
+        fw = (dirs[0][0], dirs[0][1], 0, 0)
+        bw = (dirs[1][0], dirs[1][1], 4 * h, h) if len(dirs) == 2 else None
+        ops.lstm_sequence(gates, out, frame_off, lens32, group_first, group_rows, h, fw, bw)
+        if pj is not None:
+            out = torch.tanh(split_gemm_rows(out, pj[0]).add_(pj[1]))
+        return out
+
+
 class Encoder(nn.Module):
     """Listener (asr.py:390-476): optional VGG front end + recurrent stack."""
 
@@ -271,6 +330,60 @@ class Encoder(nn.Module):
         for layer in self.layers:
             x, x_len = layer(x, x_len)
         return x, x_len
+
+    def packed_supported(self):
+        return all(isinstance(l, VGGFrontEnd) or (isinstance(l, RecurrentLayer) and l.packed_supported()) for l in self.layers)
+
+    @staticmethod
+    def _groups(t_host):
+        """CTA -> utterance grouping of the recurrent kernel: utterances arrive sorted by decreasing length;
+        long ones get small groups so that the longest sequence does not set the run time."""
+        first, rows, i, n = [], [], 0, len(t_host)
+        while i < n:
+            t = int(t_host[i])
+            r = 4 if t >= 600 else (8 if t >= 300 else 16)
+            r = min(r, n - i)
+            first.append(i)
+            rows.append(r)
+            i += r
+        return first, rows
+
+    def forward_ragged_packed(self, x, x_len, chunk=128):
+        """forward_ragged for a CUDA batch sorted by decreasing length: the front end runs in ``chunk``-utterance
+        pieces cropped to their own longest utterance, the valid frames are PACKED back to back and the
+        recurrent layers run over the packed frames (no padding is computed)."""
+        lens_host = x_len.cpu()
+        n_utts = x.shape[0]
+        front = self.layers[0] if isinstance(self.layers[0], VGGFrontEnd) else None
+        packs, tls = [], []
+        for lo in range(0, n_utts, chunk):
+            hi = min(n_utts, lo + chunk)
+            l_max = int(lens_host[lo:hi].max())
+            xc, lc = x[lo:hi, :l_max], x_len[lo:hi]
+            if front is not None:
+                if getattr(self, "split_conv", False):
+                    xc, lc = front.forward_masked_split(xc, lc)
+                else:
+                    xc, lc = front.forward_masked(xc, lc)
+            lc = lc.to(x.device).reshape(-1)
+            mask = torch.arange(xc.shape[1], device=x.device)[None, :] < lc[:, None]
+            packs.append(xc[mask])                                      # utterance-major, time ascending
+            tls.append(lc)
+        feat = torch.cat(packs, dim=0)
+        t_len = torch.cat(tls).long()
+        t_host = t_len.cpu()
+        frame_off = (torch.cumsum(t_len, 0) - t_len).to(torch.int32).contiguous()
+        lens32 = t_len.to(torch.int32).contiguous()
+        first, rows = self._groups(t_host)
+        g_first = torch.tensor(first, dtype=torch.int32, device=x.device)
+        g_rows = torch.tensor(rows, dtype=torch.int32, device=x.device)
+        for layer in self.layers:
+            if isinstance(layer, RecurrentLayer):
+                feat = layer.forward_packed(feat, frame_off, lens32, g_first, g_rows)
+        t_max = int(t_host.max())
+        enc = feat.new_zeros((n_utts, t_max, feat.shape[1]))
+        enc[torch.arange(t_max, device=x.device)[None, :] < t_len[:, None]] = feat
+        return enc, t_len
 
     def forward_ragged(self, x, x_len):
         """Batched encode of zero-padded utterances of different lengths with

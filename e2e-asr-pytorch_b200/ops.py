@@ -259,5 +259,25 @@ def conv_bias_relu_mask(y_nhwc, bias, valid_rows):
     L.check(L.load().e2e_conv_bias_relu_mask(L.ptr(y_nhwc), L.ptr(bias), L.ptr(valid_rows), n, h, w, c, 0, n * h * w, _stream()))
 
 
+def lstm_sequence(gates, out, frame_off, lens, group_first, group_rows, hidden, fw, bw=None):
+    """Packed (B)LSTM recurrence (see e2e_lstm_sequence).  gates [F, >=4H*dirs] fp32, out [F, >=H*dirs];
+    fw / bw = (bias [4H] | None, w_t [H,4,H], gate_off, out_off)."""
+    _chk(gates, F32, "gates")
+    _chk(out, F32, "out")
+    for t, nm in ((frame_off, "frame_off"), (lens, "lens"), (group_first, "group_first"), (group_rows, "group_rows")):
+        _chk(t, I32, nm)
+    dirs = [fw] + ([bw] if bw is not None else [])
+    for b, w, _, _ in dirs:
+        _chk(b, F32, "bias", 4 * hidden)
+        _chk(w, F32, "w_t", 4 * hidden * hidden)
+    if bw is None:
+        bw = (None, None, 0, 0)
+    L.check(L.load().e2e_lstm_sequence(L.ptr(gates), int(gates.stride(0)), L.ptr(out), int(out.stride(0)),
+                                      L.ptr(frame_off), L.ptr(lens), L.ptr(group_first), L.ptr(group_rows),
+                                      int(lens.numel()), int(hidden), int(group_first.numel()), len(dirs),
+                                      L.ptr(fw[0]), L.ptr(fw[1]), int(fw[2]), int(fw[3]),
+                                      L.ptr(bw[0]), L.ptr(bw[1]), int(bw[2]), int(bw[3]), _stream()))
+
+
 def launch_count():
     return int(L.load().e2e_launch_count())

@@ -240,6 +240,10 @@ class BatchedStepper:
         n_utts = feats.shape[0]
         if n_utts == 1:
             enc, enc_len = enc_mod(feats, lens)
+        elif self.split_conv and feats.is_cuda and hasattr(enc_mod, "forward_ragged_packed") and enc_mod.packed_supported():
+            # device path: split-bf16 convolutions, packed frames, persistent recurrent kernel (model.py)
+            enc_mod.split_conv = True
+            enc, enc_len = enc_mod.forward_ragged_packed(feats, lens, chunk)
         elif hasattr(enc_mod, "forward_ragged"):
             enc_mod.split_conv = self.split_conv and feats.is_cuda
             lens_host = lens.cpu()

@@ -232,6 +232,22 @@ int e2e_conv3x3_unfold_split(const float *in_nhwc, const int *valid_rows, int N,
 int e2e_conv_bias_relu_mask(float *y_nhwc, const float *bias, const int *valid_rows, int N, int H, int W, int C,
                             long long first_pixel, long long n_pixels, void *stream);
 
+/* (next) Whole-sequence LSTM recurrence of an encoder layer (RNNLayer, src/module.py:1003-1081:
+ * nn.LSTM, optionally bidirectional) over PACKED utterances, one persistent launch per layer:
+ *   for every utterance n, direction d and its frames t in walking order (d = 0: 0..len-1, d = 1: len-1..0)
+ *     z = gates[frame_off[n] + t][gate_off_d : gate_off_d + 4H] + bias_d + W_hh_d h_prev      (gate order i,f,g,o)
+ *     c = sigmoid(z_f) c_prev + sigmoid(z_i) tanh(z_g);  h = sigmoid(z_o) tanh(c);  out[frame_off[n] + t][out_off_d : +H] = h
+ *   from zero initial state.  gates = x W_ih^T of all packed frames is the caller's (library) GEMM.
+ *   w_t_d [H][4][H] with w_t[k][g][u] = W_hh[g*H + u][k];  bias_d [4H] = b_ih + b_hh (or NULL).
+ *   group_first / group_rows [n_groups]: the CTA -> utterance grouping (rows in 1..16; utterances sorted by
+ *   decreasing length; give long utterances small groups).  n_dirs 1 or 2.  H <= 384. */
+int e2e_lstm_sequence(const float *gates, long long gates_pitch, float *out, long long out_pitch,
+                      const int *frame_off, const int *lens, const int *group_first, const int *group_rows,
+                      int N, int H, int n_groups, int n_dirs,
+                      const float *bias_fw, const float *w_t_fw, int gate_off_fw, int out_off_fw,
+                      const float *bias_bw, const float *w_t_bw, int gate_off_bw, int out_off_bw,
+                      void *stream);
+
 /* Number of kernel launches issued through this library by the calling process
  * (for bench.py's gpu_launches claim). */
 long long e2e_launch_count(void);

@@ -479,3 +479,63 @@ def test_vgg_split_conv_path_is_fp32_accurate(cuda):
     assert err_split < max(2 * err_cudnn, 2e-6 * want.abs().max().item())
     for i, l in enumerate(lens):
         assert (got[i, int(l) // 4:] == 0).all()
+
+
+@pytest.mark.parametrize("hidden,in_dim,lens", [(16, 24, [30, 22, 22, 9, 1]), (320, 64, [70, 41] + [33] * 20), (40, 12, [700, 650, 310, 12])])
+def test_lstm_sequence_matches_nn_lstm(cuda, hidden, in_dim, lens):
+    """Packed bidirectional recurrence (RecurrentLayer.forward_packed: split GEMM + persistent kernel + projection) vs
+    the layer's own per-utterance forward in float64; groups of 4 / 8 / 16 utterances are all exercised."""
+    _ops()
+    from e2e_asr_pytorch_b200.model import RecurrentLayer, Encoder, reference_init_
+    from e2e_asr_pytorch_b200.decode import _Fp32Math
+    torch.manual_seed(hidden)
+    layer = RecurrentLayer(in_dim, "LSTM", hidden, True, 0.0, False, 1, "drop", True)
+    layer.apply(reference_init_)
+    for n, p in layer.named_parameters():
+        if "bias" in n:
+            p.data.normal_(0, 0.3)
+    layer.eval()
+    g = torch.Generator().manual_seed(1)
+    xs = [torch.randn(l, in_dim, generator=g) for l in lens]
+    with torch.no_grad():
+        ref = copy_double(layer)
+        want = torch.cat([ref(x[None].double(), torch.tensor([x.shape[0]]))[0][0] for x in xs], dim=0)
+        layer.to(cuda)
+        t_len = torch.tensor(lens)
+        off = (torch.cumsum(t_len, 0) - t_len).to(torch.int32).to(cuda)
+        first, rows = Encoder._groups(t_len)
+        with _Fp32Math():
+            got = layer.forward_packed(torch.cat(xs).to(cuda), off, t_len.to(torch.int32).to(cuda),
+                                       torch.tensor(first, dtype=torch.int32, device=cuda), torch.tensor(rows, dtype=torch.int32, device=cuda))
+    err = (got.cpu().double() - want).abs().max().item()
+    print("packed BLSTM H=%d: max |gpu - fp64| = %.3g (groups %s)" % (hidden, err, sorted(set(rows))))
+    assert err < 5e-6
+
+
+def copy_double(m):
+    import copy
+    return copy.deepcopy(m).double()
+
+
+def test_packed_encoder_matches_per_utterance_calls(cuda):
+    """Encoder.forward_ragged_packed (split-bf16 VGG + packed BLSTM stack) vs one batch-1 float64 call per utterance."""
+    _ops()
+    from e2e_asr_pytorch_b200 import synth
+    from e2e_asr_pytorch_b200.decode import _Fp32Math
+    asr = synth.build_asr(31, synth.TINY_ASR_CFG, seed=0)
+    enc = asr.encoder
+    lens = [96, 92, 64, 40, 40, 12]
+    feat, fl = synth.padded_batch(list(range(len(lens))), lens)
+    with torch.no_grad():
+        ref = copy_double(enc)
+        wants = [ref(feat[i:i + 1, :n].double(), fl[i:i + 1])[0][0] for i, n in enumerate(lens)]
+        enc.to(cuda)
+        enc.split_conv = True
+        assert enc.packed_supported()
+        with _Fp32Math():
+            got, gl = enc.forward_ragged_packed(feat.to(cuda), fl.to(cuda), chunk=4)
+    assert gl.cpu().tolist() == [n // 4 for n in lens]
+    for i, w in enumerate(wants):
+        err = (got[i, :w.shape[0]].cpu().double() - w).abs().max().item()
+        assert err < 5e-6, (i, err)
+        assert (got[i, w.shape[0]:] == 0).all()
