@@ -5,7 +5,7 @@
 // GEMM (library, split-bf16, see stepper.SplitLinear) and the recurrence is one persistent launch per
 // layer: a CTA owns a group of R utterances x one direction and walks their frames; thread u owns
 // hidden unit u — its four gate columns for the R utterances live in registers (4R accumulators), the
-// recurrent weights stream from L2 in a [k][gate][unit] layout (coalesced 128-byte rows), the previous
+// recurrent weights stream from L2 in a [k][unit][gate] layout (one coalesced 16-byte load per unit per k), the previous
 // hidden states are shared-memory broadcasts ([k][R], one LDS.128 per four utterances), and the cell
 // update happens in the same thread with no exchange but the one __syncthreads per time step that
 // publishes h.  Utterances are PACKED (frame_off[n] + t): no padding is computed or stored, the
@@ -20,7 +20,7 @@ constexpr int kSeqMaxThreads = 384;     // hidden sizes up to 384 (the register 
 
 struct SeqDir {
     const float *bias;      // [4H] b_ih + b_hh (may be null)
-    const float *w_t;       // [H][4][H]: w_t[k][g][u] = w_hh[g*H + u][k]
+    const float *w_t;       // [H][H][4]: w_t[k][u][g] = w_hh[g*H + u][k]  (one 16-byte load per unit per k)
     int gate_off;           // column of this direction's 4H block inside a gates row
     int out_off;            // column of this direction's H block inside an output row
     int reverse;            // 0: t = 0..len-1, 1: t = len-1..0
@@ -62,7 +62,7 @@ __device__ __forceinline__ void lstm_seq_body(const SeqParams &p, const SeqDir &
     if (unit && d.bias)
 #pragma unroll
         for (int g = 0; g < 4; ++g) b[g] = __ldg(d.bias + g * H + u);
-    const float *wu = d.w_t + u;
+    const float4 *wu = reinterpret_cast<const float4 *>(d.w_t) + u;
 
     for (int s = 0; s < max_len; ++s) {
         const float *hc = hs + (size_t)(s & 1) * H * R;
@@ -79,11 +79,10 @@ __device__ __forceinline__ void lstm_seq_body(const SeqParams &p, const SeqDir &
                 acc[g][r] = (on && unit) ? __fadd_rn(__ldg(p.gates + (long long)row[r] * p.gates_pitch + d.gate_off + g * H + u), b[g]) : 0.0f;
         }
         if (unit) {
-#pragma unroll 2
+#pragma unroll 4
             for (int k = 0; k < H; ++k) {
-                float w[4];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) w[g] = __ldg(wu + (size_t)(k * 4 + g) * H);
+                const float4 w4 = __ldg(wu + (size_t)k * H);
+                const float w[4] = {w4.x, w4.y, w4.z, w4.w};
                 float hv[R];
 #pragma unroll
                 for (int q = 0; q < R / 4; ++q) {

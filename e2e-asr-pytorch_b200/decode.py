@@ -242,7 +242,13 @@ class BeamDecoder(nn.Module):
             mark("finalize")
             status = buf.status.cpu()
             inv = torch.as_tensor(inverse, device=dev)
-            tok, sc, ln, avg, n = (a.index_select(0, inv).cpu() for a in (tok, sc, ln, avg, n))
+            # N-best back to the host through pinned buffers (the caching host allocator reuses them)
+            dev_out = [a.index_select(0, inv) for a in (tok, sc, ln, avg, n)]
+            host_out = [torch.empty(a.shape, dtype=a.dtype, pin_memory=True) for a in dev_out]
+            for h, a in zip(host_out, dev_out):
+                h.copy_(a, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            tok, sc, ln, avg, n = host_out
             status = status[torch.as_tensor(inverse)]
 
         if self.profile_phases:

@@ -278,7 +278,8 @@ class RecurrentLayer(nn.Module):
             g = lambda n: getattr(rnn, n).detach().float()
             w_in = torch.cat([g("weight_ih_l0" + x) for x in sfx], dim=0)                       # [dirs*4H, in]
             dirs = [((g("bias_ih_l0" + x) + g("bias_hh_l0" + x)).contiguous(),
-                     g("weight_hh_l0" + x).t().contiguous()) for x in sfx]                         # w_t [H(k), 4H] == [H][4][H]
+                     g("weight_hh_l0" + x).view(4, rnn.hidden_size, rnn.hidden_size).permute(2, 1, 0).contiguous())
+                    for x in sfx]                                                                  # w_t [k][u][gate]
             pj = (SplitLinear(self.pj.weight.detach().float()), self.pj.bias.detach().float()) if self.proj else None
             cache[key] = (SplitLinear(w_in), dirs, pj)
         return cache[key]

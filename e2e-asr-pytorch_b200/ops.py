@@ -261,7 +261,7 @@ def conv_bias_relu_mask(y_nhwc, bias, valid_rows):
 
 def lstm_sequence(gates, out, frame_off, lens, group_first, group_rows, hidden, fw, bw=None):
     """Packed (B)LSTM recurrence (see e2e_lstm_sequence).  gates [F, >=4H*dirs] fp32, out [F, >=H*dirs];
-    fw / bw = (bias [4H] | None, w_t [H,4,H], gate_off, out_off)."""
+    fw / bw = (bias [4H] | None, w_t [H,H,4], gate_off, out_off)."""
     _chk(gates, F32, "gates")
     _chk(out, F32, "out")
     for t, nm in ((frame_off, "frame_off"), (lens, "lens"), (group_first, "group_first"), (group_rows, "group_rows")):

@@ -238,7 +238,7 @@ int e2e_conv_bias_relu_mask(float *y_nhwc, const float *bias, const int *valid_r
  *     z = gates[frame_off[n] + t][gate_off_d : gate_off_d + 4H] + bias_d + W_hh_d h_prev      (gate order i,f,g,o)
  *     c = sigmoid(z_f) c_prev + sigmoid(z_i) tanh(z_g);  h = sigmoid(z_o) tanh(c);  out[frame_off[n] + t][out_off_d : +H] = h
  *   from zero initial state.  gates = x W_ih^T of all packed frames is the caller's (library) GEMM.
- *   w_t_d [H][4][H] with w_t[k][g][u] = W_hh[g*H + u][k];  bias_d [4H] = b_ih + b_hh (or NULL).
+ *   w_t_d [H][H][4] with w_t[k][u][g] = W_hh[g*H + u][k] (16-byte aligned);  bias_d [4H] = b_ih + b_hh (or NULL).
  *   group_first / group_rows [n_groups]: the CTA -> utterance grouping (rows in 1..16; utterances sorted by
  *   decreasing length; give long utterances small groups).  n_dirs 1 or 2.  H <= 384. */
 int e2e_lstm_sequence(const float *gates, long long gates_pitch, float *out, long long out_pitch,
