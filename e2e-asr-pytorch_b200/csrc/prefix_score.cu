@@ -30,6 +30,7 @@
 //   copied into a staging buffer with cp.async (LDGSTS) before tile k is computed and turned into
 //   phi afterwards, so one __syncthreads per tile is all the synchronisation there is.
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 #include <cuda.h>      // CUtensorMap (types only; the encoder is fetched from the driver at run time)
 
@@ -375,7 +376,11 @@ extern "C" int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int
     // A small launch cannot fill the machine and its duration is the longest utterance's chain:
     // spread every utterance over one-warp CTAs so that each warp has a scheduler to itself.
     // (Every lane computes the same values whatever the split.)
-    if (nl > 32 && (long long)n_run * ((LU + nl - 1) / nl) < 2 * 148) nl = 32;
+    static const long long split_below = []() {
+        const char *e = getenv("E2E_PREFIX_SPLIT_BELOW");        // tuning knob: CTAs (at full width) below which to split
+        return e ? atoll(e) : 2LL * 148;
+    }();
+    if (nl > 32 && (long long)n_run * ((LU + nl - 1) / nl) < split_below) nl = 32;
     PrefixParams p;
     p.x = x; p.Tmax = Tmax; p.U = U; p.Vp = Vp; p.V = V; p.enc_len = enc_len;
     p.r_prev = reinterpret_cast<const float2 *>(r_prev); p.lanes_prev = lanes_prev;
