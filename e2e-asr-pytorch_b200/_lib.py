@@ -63,6 +63,9 @@ SIGNATURES = {
     "e2e_lstm_sequence": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int, c_int, c_int, c_int,
                                   c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "e2e_conv1_direct": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_void_p]),
+    "e2e_conv_bias_relu_mask_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "e2e_beam_finalize": (c_int, [c_int, c_int, c_void_p,
                                   c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p,

@@ -137,3 +137,135 @@ extern "C" int e2e_conv_bias_relu_mask(float *y_nhwc, const float *bias, const i
     count_launch();
     return check_launch("e2e_conv_bias_relu_mask");
 }
+
+// ---------------------------------------------------------------------------------------------
+// First VGG layer (Cin -> Cout, 3x3 "same", bias, ReLU; src/module.py:672-674) straight from the
+// feature frames into NHWC, and bias + ReLU + mask fused with the 2x2 ceil-mode max pooling
+// (src/module.py:676,683) for the layers that are followed by one.
+// ---------------------------------------------------------------------------------------------
+namespace e2e {
+
+// feat [N][L][Cin*F] (frame t = Cin blocks of F frequency bins, src/module.py:688-690), weight [Cout][Cin][3][3],
+// out [N][L][F][Cout] NHWC = relu(conv + bias).  Input rows t >= valid[n] read as zero.  One CTA per (n, t) row:
+// the three input rows sit in shared memory, the weights as [tap][cin][cout] (one LDS.128 per 4 output channels);
+// lane <-> 4 output channels, so a warp writes one pixel's channels as 512 contiguous bytes.
+constexpr int kC1Rows = 4;       // output rows per CTA (the weights are staged once per CTA)
+
+__global__ void __launch_bounds__(256)
+conv1_direct_kernel(const float *__restrict__ feat, long long feat_pitch_n, const float *__restrict__ weight,
+                    const float *__restrict__ bias, const int *__restrict__ valid, int L, int F, int Cin, int Cout,
+                    float *__restrict__ out)
+{
+    extern __shared__ __align__(16) float c1_smem[];
+    float *ws = c1_smem;                                   // [9*Cin][Cout]
+    float *rows = ws + 9 * Cin * Cout;                     // [kC1Rows + 2][Cin][F + 2] (zero halo in frequency)
+    const int n = blockIdx.y, t0 = blockIdx.x * kC1Rows, tid = threadIdx.x;
+    const int Fp = F + 2;
+    for (int i = tid; i < 9 * Cin * Cout; i += blockDim.x) {
+        const int co = i % Cout, r = i / Cout;             // r = tap*Cin + ci
+        const int ci = r % Cin, tap = r / Cin;
+        ws[i] = __ldg(weight + ((size_t)co * Cin + ci) * 9 + tap);
+    }
+    const int vr = __ldg(valid + n);
+    for (int i = tid; i < (kC1Rows + 2) * Cin * Fp; i += blockDim.x) {
+        const int f = i % Fp - 1, r = i / Fp;              // r = row*Cin + ci
+        const int ci = r % Cin, row = r / Cin;
+        const int ts = t0 + row - 1;
+        float v = 0.0f;
+        if (f >= 0 && f < F && ts >= 0 && ts < L && ts < vr) v = __ldg(feat + (size_t)n * feat_pitch_n + (size_t)ts * Cin * F + ci * F + f);
+        rows[i] = v;
+    }
+    __syncthreads();
+    const int C4 = Cout >> 2;
+    for (int i = tid; i < kC1Rows * F * C4; i += blockDim.x) {
+        const int c4 = i % C4;
+        const int f = (i / C4) % F, tr = i / (C4 * F);
+        const int t = t0 + tr;
+        if (t >= L) break;
+        float4 acc = __ldg(reinterpret_cast<const float4 *>(bias) + c4);
+        for (int dy = 0; dy < 3; ++dy)
+            for (int ci = 0; ci < Cin; ++ci) {
+                const float *rp = rows + ((tr + dy) * Cin + ci) * Fp + f;   // f-1 .. f+1 with the halo offset
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const float x = rp[dx];
+                    const float4 w = *reinterpret_cast<const float4 *>(ws + ((dy * 3 + dx) * Cin + ci) * Cout + c4 * 4);
+                    acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y); acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
+                }
+            }
+        acc.x = fmaxf(acc.x, 0.0f); acc.y = fmaxf(acc.y, 0.0f); acc.z = fmaxf(acc.z, 0.0f); acc.w = fmaxf(acc.w, 0.0f);
+        *reinterpret_cast<float4 *>(out + (((size_t)n * L + t) * F + f) * Cout + c4 * 4) = acc;
+    }
+}
+
+// y [N][H][W][C] (GEMM result) -> out [N][ceil(H/2)][ceil(W/2)][C] = maxpool2x2_ceil( mask(relu(y + bias)) )
+__global__ void __launch_bounds__(256)
+bias_relu_mask_pool_kernel(const float *__restrict__ y, const float *__restrict__ bias, const int *__restrict__ valid,
+                           int N, int H, int W, int C, float *__restrict__ out)
+{
+    const int C4 = C >> 2, H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
+    const long long total = (long long)N * H2 * W2 * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        long long r = i / C4;
+        const int w2 = (int)(r % W2); r /= W2;
+        const int h2 = (int)(r % H2);
+        const int n = (int)(r / H2);
+        const int vr = __ldg(valid + n);
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(bias) + c4);
+        float4 m = make_float4(0.0f, 0.0f, 0.0f, 0.0f);              // relu output >= 0 and masked rows are 0
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            const int h = 2 * h2 + dy;
+            if (h >= H || h >= vr) continue;
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int w = 2 * w2 + dx;
+                if (w >= W) continue;
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(y + (((long long)n * H + h) * W + w) * C) + c4);
+                m.x = fmaxf(m.x, __fadd_rn(v.x, b.x)); m.y = fmaxf(m.y, __fadd_rn(v.y, b.y));
+                m.z = fmaxf(m.z, __fadd_rn(v.z, b.z)); m.w = fmaxf(m.w, __fadd_rn(v.w, b.w));
+            }
+        }
+        reinterpret_cast<float4 *>(out)[i] = m;
+    }
+}
+
+}  // namespace e2e
+
+extern "C" int e2e_conv1_direct(const float *feat, long long feat_pitch_n, const float *weight, const float *bias,
+                                const int *valid_rows, int N, int L, int F, int Cin, int Cout, float *out_nhwc, void *stream)
+{
+    using namespace e2e;
+    if (!feat || !weight || !bias || !valid_rows || !out_nhwc) return set_error(E2E_ERR_ARG, "e2e_conv1_direct: null pointer");
+    if (N <= 0 || L <= 0 || F <= 0 || Cin <= 0 || Cout <= 0 || (Cout & 3) || N > 65535 || feat_pitch_n < (long long)L * Cin * F)
+        return set_error(E2E_ERR_ARG, "e2e_conv1_direct: bad size (Cout must be a multiple of 4, N <= 65535)");
+    if ((reinterpret_cast<uintptr_t>(bias) & 15) || (reinterpret_cast<uintptr_t>(out_nhwc) & 15))
+        return set_error(E2E_ERR_ARG, "e2e_conv1_direct: misaligned buffer");
+    const size_t smem = ((size_t)9 * Cin * Cout + (size_t)(kC1Rows + 2) * Cin * (F + 2) + 4) * 4;
+    if (smem > 200 * 1024) return set_error(E2E_ERR_UNSUPPORTED, "e2e_conv1_direct: %zu bytes of shared memory needed", smem);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(conv1_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(E2E_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    conv1_direct_kernel<<<dim3((L + kC1Rows - 1) / kC1Rows, N), 256, smem, static_cast<cudaStream_t>(stream)>>>(feat, feat_pitch_n, weight, bias, valid_rows,
+                                                                                      L, F, Cin, Cout, out_nhwc);
+    count_launch();
+    return check_launch("e2e_conv1_direct");
+}
+
+extern "C" int e2e_conv_bias_relu_mask_pool(const float *y_nhwc, const float *bias, const int *valid_rows, int N, int H, int W, int C,
+                                            float *out_nhwc, void *stream)
+{
+    using namespace e2e;
+    if (!y_nhwc || !bias || !valid_rows || !out_nhwc) return set_error(E2E_ERR_ARG, "e2e_conv_bias_relu_mask_pool: null pointer");
+    if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return set_error(E2E_ERR_ARG, "e2e_conv_bias_relu_mask_pool: bad size");
+    if ((reinterpret_cast<uintptr_t>(y_nhwc) & 15) || (reinterpret_cast<uintptr_t>(bias) & 15) || (reinterpret_cast<uintptr_t>(out_nhwc) & 15))
+        return set_error(E2E_ERR_ARG, "e2e_conv_bias_relu_mask_pool: misaligned buffer");
+    const long long total = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    bias_relu_mask_pool_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(y_nhwc, bias, valid_rows, N, H, W, C, out_nhwc);
+    count_launch();
+    return check_launch("e2e_conv_bias_relu_mask_pool");
+}

@@ -148,8 +148,9 @@ class VGGFrontEnd(nn.Module):
             cache[key] = SplitLinear(w2d)
         return cache[key]
 
-    def _conv_split(self, x, valid, conv):
-        """x [N,H,W,C] fp32 NHWC, valid [N] int32 -> relu(conv(x) + b) [N,H,W,Cout] NHWC, rows >= valid zeroed."""
+    def _conv_split(self, x, valid, conv, pool=False):
+        """x [N,H,W,C] fp32 NHWC, valid [N] int32 -> relu(conv(x) + b) [N,H,W,Cout] NHWC, rows >= valid zeroed;
+        with ``pool`` the 2x2 ceil-mode max pooling that follows is fused into the epilogue kernel."""
         from . import ops
         n, h, w, c = x.shape
         k = 9 * c
@@ -166,30 +167,33 @@ class VGGFrontEnd(nn.Module):
             torch.addmm(ym, am[:, :2 * k], lin.b1, out_dtype=torch.float32, out=ym)    # + a1w2 + a2w1
             torch.addmm(ym, am[:, :k], lin.b0, out_dtype=torch.float32, out=ym)        # + a1w1
         y = y.view(n, h, w, conv.out_channels)
-        ops.conv_bias_relu_mask(y, conv.bias.detach().float().contiguous(), valid)
+        bias = conv.bias.detach().float().contiguous()
+        if pool:
+            return ops.conv_bias_relu_mask_pool(y, bias, valid)
+        ops.conv_bias_relu_mask(y, bias, valid)
         return y
 
     def forward_masked_split(self, feat, feat_len):
-        """forward_masked with the three wide convolutions (128->128, 128->256, 256->256: 98 % of the
-        front end's FLOPs) on the tensor cores: activations stay NHWC, each layer is unfold+split
-        (csrc/conv_split.cu) -> three bf16 GEMMs with fp32 accumulation -> bias/ReLU/mask kernel.  The
-        4->128 layer (K = 36) and the pooling stay library calls."""
-        img = self._as_image(feat)
-        n, _, t, _ = img.shape
-        own = (feat_len // 4 * 4).to(img.device)
+        """forward_masked on the device path: the 4->128 layer is a direct kernel from the feature frames
+        into NHWC, the three wide convolutions (128->128, 128->256, 256->256: 98 % of the front end's FLOPs)
+        run on the tensor cores — unfold+split (csrc/conv_split.cu) -> three bf16 GEMMs with fp32
+        accumulation -> bias/ReLU/mask(/2x2 max-pool) kernel — and the activations stay NHWC throughout."""
+        from . import ops
+        drop = feat.shape[1] % 4
+        if drop:
+            feat = feat[:, :-drop, :]
+        if feat.stride(2) != 1 or feat.stride(1) != feat.shape[2]:
+            feat = feat.contiguous()
+        own = (feat_len // 4 * 4).to(feat.device)
         v1 = own.to(torch.int32).contiguous()
         v2 = (own // 2).to(torch.int32).contiguous()
         convs = [m for m in self.extractor if isinstance(m, nn.Conv2d)]
-        mask = (torch.arange(t, device=img.device)[None, :] < own[:, None])[:, None, :, None].to(img.dtype)
-        x = (img * mask).contiguous(memory_format=torch.channels_last)
-        y = F.relu(F.conv2d(x, convs[0].weight, convs[0].bias, padding=1))             # cuDNN, channels_last
-        y = y.permute(0, 2, 3, 1).contiguous()                                         # NHWC (a view when cuDNN kept channels_last)
-        y = self._conv_split(y, v1, convs[1])                                          # rows >= own read as zero inside
-        y = F.max_pool2d(y.permute(0, 3, 1, 2), 2, stride=2, ceil_mode=True).permute(0, 2, 3, 1).contiguous()
+        w1 = convs[0].weight.detach().float().contiguous()
+        y = ops.conv1_direct(feat, w1, convs[0].bias.detach().float().contiguous(), v1, self.freq_dim)   # [N,L,F,C1]
+        y = self._conv_split(y, v1, convs[1], pool=True)                               # rows >= own read as zero inside
         y = self._conv_split(y, v2, convs[2])
-        y = self._conv_split(y, v2, convs[3])
-        y = F.max_pool2d(y.permute(0, 3, 1, 2), 2, stride=2, ceil_mode=True)           # [N, C2, T/4, F/4]
-        out = y.permute(0, 2, 1, 3).contiguous()                                       # [N, T/4, C2, F/4]
+        y = self._conv_split(y, v2, convs[3], pool=True)                               # [N, T/4, F/4, C2]
+        out = y.permute(0, 1, 3, 2).contiguous()                                       # [N, T/4, C2, F/4]
         return out.view(out.shape[0], out.shape[1], self.out_dim), feat_len // 4
 
 

@@ -279,5 +279,34 @@ def lstm_sequence(gates, out, frame_off, lens, group_first, group_rows, hidden, 
                                       L.ptr(bw[0]), L.ptr(bw[1]), int(bw[2]), int(bw[3]), _stream()))
 
 
+def conv1_direct(feat, weight, bias, valid_rows, n_freq):
+    """First VGG layer from the feature frames: feat [N,L,Cin*F] (last dim contiguous, rows of an utterance contiguous)
+    -> relu(conv + bias) [N,L,F,Cout] NHWC."""
+    _chk(weight, F32, "weight")
+    _chk(bias, F32, "bias")
+    _chk(valid_rows, I32, "valid_rows", feat.shape[0])
+    if not feat.is_cuda or feat.dtype != F32 or feat.stride(2) != 1 or feat.stride(1) != feat.shape[2]:
+        raise ValueError("conv1_direct: feat must be a CUDA fp32 [N,L,D] tensor with contiguous utterances")
+    n, l, d = feat.shape
+    cout, cin = weight.shape[0], weight.shape[1]
+    if d != cin * n_freq:
+        raise ValueError("conv1_direct: feature width %d != Cin*F" % d)
+    out = torch.empty((n, l, n_freq, cout), dtype=F32, device=feat.device)
+    L.check(L.load().e2e_conv1_direct(L.ptr(feat), int(feat.stride(0)), L.ptr(weight), L.ptr(bias), L.ptr(valid_rows),
+                                     n, l, int(n_freq), int(cin), int(cout), L.ptr(out), _stream()))
+    return out
+
+
+def conv_bias_relu_mask_pool(y_nhwc, bias, valid_rows):
+    """max_pool2d(2, 2, ceil_mode=True) of mask(relu(y + bias)); y [N,H,W,C] NHWC -> [N,ceil(H/2),ceil(W/2),C]."""
+    _chk(y_nhwc, F32, "y_nhwc")
+    _chk(bias, F32, "bias", y_nhwc.shape[3])
+    _chk(valid_rows, I32, "valid_rows", y_nhwc.shape[0])
+    n, h, w, c = y_nhwc.shape
+    out = torch.empty((n, (h + 1) // 2, (w + 1) // 2, c), dtype=F32, device=y_nhwc.device)
+    L.check(L.load().e2e_conv_bias_relu_mask_pool(L.ptr(y_nhwc), L.ptr(bias), L.ptr(valid_rows), n, h, w, c, L.ptr(out), _stream()))
+    return out
+
+
 def launch_count():
     return int(L.load().e2e_launch_count())

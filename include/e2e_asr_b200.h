@@ -248,6 +248,17 @@ int e2e_lstm_sequence(const float *gates, long long gates_pitch, float *out, lon
                       const float *bias_bw, const float *w_t_bw, int gate_off_bw, int out_off_bw,
                       void *stream);
 
+/* First VGG layer (Conv2d Cin->Cout 3x3 "same" + bias + ReLU, src/module.py:672-674) straight from the feature
+ * frames: feat [N][L][Cin*F] (a frame is Cin blocks of F bins, src/module.py:688-690; row pitch of an utterance
+ * feat_pitch_n floats), weight [Cout][Cin][3][3], out [N][L][F][Cout] NHWC.  Input rows t >= valid_rows[n] read as 0. */
+int e2e_conv1_direct(const float *feat, long long feat_pitch_n, const float *weight, const float *bias,
+                     const int *valid_rows, int N, int L, int F, int Cin, int Cout, float *out_nhwc, void *stream);
+
+/* e2e_conv_bias_relu_mask fused with the 2x2 stride-2 ceil-mode max pooling that follows the 2nd and 4th
+ * convolution (src/module.py:676,683): out [N][ceil(H/2)][ceil(W/2)][C] from the GEMM result y [N][H][W][C]. */
+int e2e_conv_bias_relu_mask_pool(const float *y_nhwc, const float *bias, const int *valid_rows, int N, int H, int W, int C,
+                                 float *out_nhwc, void *stream);
+
 /* Number of kernel launches issued through this library by the calling process
  * (for bench.py's gpu_launches claim). */
 long long e2e_launch_count(void);

@@ -539,3 +539,28 @@ def test_packed_encoder_matches_per_utterance_calls(cuda):
         err = (got[i, :w.shape[0]].cpu().double() - w).abs().max().item()
         assert err < 5e-6, (i, err)
         assert (got[i, w.shape[0]:] == 0).all()
+
+
+def test_conv1_direct_and_fused_pool_match_torch(cuda):
+    """First VGG layer straight from the frames (NHWC out) vs F.conv2d on the masked image; bias+ReLU+mask+2x2
+    ceil-mode pooling vs the torch ops, odd sizes included."""
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(3)
+    n, l, cin, f, cout = 3, 11, 4, 7, 8
+    feat = torch.randn(n, l + 2, cin * f, generator=g)[:, :l]                    # non-contiguous utterances
+    w = torch.randn(cout, cin, 3, 3, generator=g) * 0.3
+    b = torch.randn(cout, generator=g)
+    valid = torch.tensor([11, 5, 8], dtype=torch.int32)
+    img = feat.reshape(n, l, cin, f).transpose(1, 2).clone()                     # [N, Cin, L, F]
+    for i in range(n):
+        img[i, :, int(valid[i]):] = 0
+    want = torch.relu(torch.nn.functional.conv2d(img.double(), w.double(), b.double(), padding=1)).permute(0, 2, 3, 1)
+    got = ops.conv1_direct(feat.to(cuda), w.to(cuda), b.to(cuda), valid.to(cuda), f).cpu()
+    assert (got.double() - want).abs().max().item() < 1e-5
+    y = torch.randn(n, l, f, cout, generator=g)
+    ref = torch.relu(y + b)
+    for i in range(n):
+        ref[i, int(valid[i]):] = 0
+    ref = torch.nn.functional.max_pool2d(ref.permute(0, 3, 1, 2), 2, stride=2, ceil_mode=True).permute(0, 2, 3, 1)
+    out = ops.conv_bias_relu_mask_pool(y.to(cuda), b.to(cuda), valid.to(cuda)).cpu()
+    assert out.shape == ref.shape and torch.equal(out, ref.contiguous())
