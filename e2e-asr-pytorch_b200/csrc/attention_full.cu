@@ -328,7 +328,7 @@ extern "C" int e2e_attention_loc_full(const float *key_t, const float *value, co
     if ((reinterpret_cast<uintptr_t>(value) & 15) || (reinterpret_cast<uintptr_t>(ctx) & 15) || (reinterpret_cast<uintptr_t>(attn) & 15))
         return set_error(E2E_ERR_ARG, "e2e_attention_loc_full: value, attn and ctx must be 16-byte aligned");
     int NB = hyps_per_unit;
-    if (NB <= 0) NB = 2;
+    if (NB <= 0) NB = n_run >= 2 * 148 ? 4 : 2;       // big launches: more reuse per constant load; small ones: more units
     if (NB != 1 && NB != 2 && NB != 4) return set_error(E2E_ERR_ARG, "e2e_attention_loc_full: hyps_per_unit must be 0, 1, 2 or 4");
     while (NB > 1 && NB / 2 >= B) NB /= 2;
     AttFullParams p;
