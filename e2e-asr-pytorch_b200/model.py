@@ -1,8 +1,9 @@
-"""Plain-PyTorch acoustic model + RNNLM with the reference's module tree.
+"""Acoustic model + RNNLM with the reference's module tree.
 
-These modules are NOT the accelerated path.  north_star keeps the VGG/BLSTM
-encoder, the location-aware attention decoder step and the RNNLM LSTM step as
-cuBLAS/cuDNN-backed PyTorch; they exist here so that
+The ``forward`` methods are plain PyTorch restatements of the reference modules (north_star keeps
+the encoder, the attention decoder step and the RNNLM step library backed); the ``*_split`` /
+``*_packed`` methods are the device path of the encoder (library GEMMs on an
+exact bf16 split + hand-written kernels for everything around them).  The modules exist here so that
 
 * ``bench.py`` / ``smoke()`` can build the BASELINE configs on the GPU box,
   where ``/root/reference`` is absent, with random-init weights, and

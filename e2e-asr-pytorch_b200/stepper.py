@@ -1,10 +1,10 @@
-"""Batched (utterance x beam) model step in plain PyTorch.
+"""Batched (utterance x beam) model step.
 
-north_star keeps the encoder, the location-aware attention decoder step and the
-RNNLM step as cuBLAS/cuDNN-backed PyTorch.  The reference runs them one
-hypothesis at a time on batch-1 tensors and bounces every state through the
-CPU (src/decode.py:105-123,144-151,265-277); here the same arithmetic runs once
-per decode step over all N = U*B hypotheses with device-resident states:
+north_star keeps the dense contractions of the encoder, the attention decoder
+step and the RNNLM step as library (cuBLAS) GEMMs.  The reference runs these
+modules one hypothesis at a time on batch-1 tensors and bounces every state
+through the CPU (src/decode.py:105-123,144-151,265-277); here the same arithmetic
+runs once per decode step over all N = U*B hypotheses with device-resident states:
 
 * attention  (src/asr.py:333-364, src/module.py:1152-1173 / :1120-1132)
 * speller    (src/asr.py:259-266)
@@ -14,7 +14,9 @@ The stepper reads the weights straight out of the ``asr`` / ``lm`` modules it is
 given (parameter names of the reference), so it works with the reference's own
 objects as well as with ``model.py``.
 
-Two things keep the library GEMMs off the critical path without leaving fp32:
+On a GPU everything around the GEMMs is hand-written (csrc/attention_full.cu,
+csrc/lstm_step.cu, csrc/conv_split.cu, csrc/lstm_seq.cu); on the CPU (host-logic tests only) the plain
+PyTorch restatement below runs.  What keeps the step fast without leaving fp32:
 
 * utterances arrive sorted by decreasing length, so the ones still decoding are
   always a PREFIX of the batch; every step only touches the first ``k`` of them;
@@ -27,7 +29,9 @@ Two things keep the library GEMMs off the critical path without leaving fp32:
 * ``fused_attention``: the location-aware energies + masked softmax run in one
   hand-written kernel (csrc/attention_full.cu: location convolution, energies, masked
   softmax and the context product) instead of a cuDNN convolution, ~8 passes over
-  [U*B, T, 300] temporaries and a batched GEMM, and never touches padded frames.
+  [U*B, T, 300] temporaries and a batched GEMM, and never touches padded frames;
+* the LSTM states are never permuted: a step reads them through the parents' row index
+  (``_FusedLstm``), and the encoder runs over packed frames (``model.Encoder.forward_ragged_packed``).
 """
 import numpy as np
 import torch
