@@ -158,9 +158,9 @@ conv1_direct_kernel(const float *__restrict__ feat, long long feat_pitch_n, cons
 {
     extern __shared__ __align__(16) float c1_smem[];
     float *ws = c1_smem;                                   // [9*Cin][Cout]
-    float *rows = ws + 9 * Cin * Cout;                     // [kC1Rows + 2][Cin][F + 2] (zero halo in frequency)
+    float *rows = ws + 9 * Cin * Cout;                     // [kC1Rows + 2][Cin][F + 5] (zero halo in frequency + pad)
     const int n = blockIdx.y, t0 = blockIdx.x * kC1Rows, tid = threadIdx.x;
-    const int Fp = F + 2;
+    const int Fp = F + 5;
     for (int i = tid; i < 9 * Cin * Cout; i += blockDim.x) {
         const int co = i % Cout, r = i / Cout;             // r = tap*Cin + ci
         const int ci = r % Cin, tap = r / Cin;
@@ -176,25 +176,42 @@ conv1_direct_kernel(const float *__restrict__ feat, long long feat_pitch_n, cons
         rows[i] = v;
     }
     __syncthreads();
-    const int C4 = Cout >> 2;
-    for (int i = tid; i < kC1Rows * F * C4; i += blockDim.x) {
-        const int c4 = i % C4;
-        const int f = (i / C4) % F, tr = i / (C4 * F);
-        const int t = t0 + tr;
-        if (t >= L) break;
-        float4 acc = __ldg(reinterpret_cast<const float4 *>(bias) + c4);
-        for (int dy = 0; dy < 3; ++dy)
-            for (int ci = 0; ci < Cin; ++ci) {
-                const float *rp = rows + ((tr + dy) * Cin + ci) * Fp + f;   // f-1 .. f+1 with the halo offset
+    // lane <-> 4 output channels, warp <-> a run of 4 pixels of one row: per (dy, cin) 6 broadcast inputs and
+    // 3 weight quads feed 48 FMAs
+    const int C4 = Cout >> 2, FG = (F + 3) >> 2;
+    const int lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+    for (int c4 = lane; c4 < C4; c4 += 32) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias) + c4);
+        for (int item = warp; item < kC1Rows * FG; item += n_warps) {
+            const int tr = item / FG, f0 = (item - tr * FG) * 4;
+            const int t = t0 + tr;
+            if (t >= L) break;
+            float4 acc[4] = {b4, b4, b4, b4};
+            for (int dy = 0; dy < 3; ++dy)
+                for (int ci = 0; ci < Cin; ++ci) {
+                    const float *rp = rows + ((tr + dy) * Cin + ci) * Fp + f0;       // bins f0-1 .. f0+4 with the halo offset
+                    float x[6];
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const float x = rp[dx];
-                    const float4 w = *reinterpret_cast<const float4 *>(ws + ((dy * 3 + dx) * Cin + ci) * Cout + c4 * 4);
-                    acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y); acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
+                    for (int q = 0; q < 6; ++q) x[q] = rp[q];
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const float4 w = *reinterpret_cast<const float4 *>(ws + ((dy * 3 + dx) * Cin + ci) * Cout + c4 * 4);
+#pragma unroll
+                        for (int px = 0; px < 4; ++px) {
+                            acc[px].x = fmaf(x[px + dx], w.x, acc[px].x); acc[px].y = fmaf(x[px + dx], w.y, acc[px].y);
+                            acc[px].z = fmaf(x[px + dx], w.z, acc[px].z); acc[px].w = fmaf(x[px + dx], w.w, acc[px].w);
+                        }
+                    }
+                }
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+                if (f0 + px < F) {
+                    float4 a = acc[px];
+                    a.x = fmaxf(a.x, 0.0f); a.y = fmaxf(a.y, 0.0f); a.z = fmaxf(a.z, 0.0f); a.w = fmaxf(a.w, 0.0f);
+                    *reinterpret_cast<float4 *>(out + (((size_t)n * L + t) * F + f0 + px) * Cout + c4 * 4) = a;
                 }
             }
-        acc.x = fmaxf(acc.x, 0.0f); acc.y = fmaxf(acc.y, 0.0f); acc.z = fmaxf(acc.z, 0.0f); acc.w = fmaxf(acc.w, 0.0f);
-        *reinterpret_cast<float4 *>(out + (((size_t)n * L + t) * F + f) * Cout + c4 * 4) = acc;
+        }
     }
 }
 
@@ -242,7 +259,7 @@ extern "C" int e2e_conv1_direct(const float *feat, long long feat_pitch_n, const
         return set_error(E2E_ERR_ARG, "e2e_conv1_direct: bad size (Cout must be a multiple of 4, N <= 65535)");
     if ((reinterpret_cast<uintptr_t>(bias) & 15) || (reinterpret_cast<uintptr_t>(out_nhwc) & 15))
         return set_error(E2E_ERR_ARG, "e2e_conv1_direct: misaligned buffer");
-    const size_t smem = ((size_t)9 * Cin * Cout + (size_t)(kC1Rows + 2) * Cin * (F + 2) + 4) * 4;
+    const size_t smem = ((size_t)9 * Cin * Cout + (size_t)(kC1Rows + 2) * Cin * (F + 5) + 4) * 4;
     if (smem > 200 * 1024) return set_error(E2E_ERR_UNSUPPORTED, "e2e_conv1_direct: %zu bytes of shared memory needed", smem);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(conv1_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
