@@ -93,6 +93,7 @@ struct CombineParams {
     float w_ctc, w_att, w_lm, eos_threshold; int flags;
     int *n_live, *n_active, *last_tok, *prefix_len; float *score_sum, *ctc_prob; int *prev_lane;
     int *parent_slot, *hist_tok, *hist_parent; float *hist_score;
+    long long *parent_row, *last_tok64;     // optional 64-bit copies for the host's gathers (row = u*B + parent slot)
     int *fin_count, *fin_step, *fin_parent; float *fin_sum, *fin_score; int fin_cap;
     int *status;
 };
@@ -107,7 +108,10 @@ beam_combine_prune_kernel(const CombineParams p)
     int *out_parent = p.parent_slot + (long long)u * B;
     const bool idle = p.step >= p.max_len[u];
     if (idle) {
-        for (int i = threadIdx.x; i < B; i += blockDim.x) out_parent[i] = i;
+        for (int i = threadIdx.x; i < B; i += blockDim.x) {
+            out_parent[i] = i;
+            if (p.parent_row) p.parent_row[(long long)u * B + i] = (long long)u * B + i;
+        }
         return;
     }
     const bool use_ctc = (p.flags & E2E_BEAM_USE_CTC) != 0, use_lm = (p.flags & E2E_BEAM_USE_LM) != 0;
@@ -270,6 +274,8 @@ beam_combine_prune_kernel(const CombineParams p)
         if (rank < B) {
             const int o = u * B + rank;
             p.last_tok[o] = c_tok[i];
+            if (p.last_tok64) p.last_tok64[o] = c_tok[i];
+            if (p.parent_row) p.parent_row[o] = (long long)u * B + b;
             p.prefix_len[o] = p.step + 1;
             p.score_sum[o] = c_sum[i];
             p.ctc_prob[o] = c_psi[i];
@@ -282,6 +288,7 @@ beam_combine_prune_kernel(const CombineParams p)
     }
     for (int i = keep + threadIdx.x; i < B; i += blockDim.x) {      // unused slots: keep gathers in range
         out_parent[i] = 0;
+        if (p.parent_row) p.parent_row[(long long)u * B + i] = (long long)u * B;
         p.hist_tok[hrow + i] = 0;
         p.hist_parent[hrow + i] = 0;
         p.hist_score[hrow + i] = 0.0f;
@@ -383,7 +390,8 @@ extern "C" int e2e_beam_combine_prune(const float *att_logits, int ld_att, const
                                       int *parent_slot,
                                       int *hist_tok, int *hist_parent, float *hist_score,
                                       int *fin_count, int *fin_step, int *fin_parent, float *fin_sum, float *fin_score,
-                                      int fin_cap, int *status, int n_run, void *stream)
+                                      int fin_cap, int *status, int n_run,
+                                      long long *parent_row, long long *last_tok64, void *stream)
 {
     using namespace e2e;
     const bool use_ctc = (flags & E2E_BEAM_USE_CTC) != 0, use_lm = (flags & E2E_BEAM_USE_LM) != 0;
@@ -404,6 +412,7 @@ extern "C" int e2e_beam_combine_prune(const float *att_logits, int ld_att, const
     p.flags = flags;
     p.n_live = n_live; p.n_active = n_active; p.last_tok = last_tok; p.prefix_len = prefix_len; p.score_sum = score_sum; p.ctc_prob = ctc_prob; p.prev_lane = prev_lane;
     p.parent_slot = parent_slot; p.hist_tok = hist_tok; p.hist_parent = hist_parent; p.hist_score = hist_score;
+    p.parent_row = parent_row; p.last_tok64 = last_tok64;
     p.fin_count = fin_count; p.fin_step = fin_step; p.fin_parent = fin_parent; p.fin_sum = fin_sum; p.fin_score = fin_score;
     p.fin_cap = fin_cap; p.status = status;
     const size_t smem = combine_smem_bytes(B, p.C);

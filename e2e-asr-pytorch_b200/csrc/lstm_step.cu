@@ -56,6 +56,35 @@ lstm_split_rows_kernel(const float *__restrict__ src, long long src_pitch, const
     }
 }
 
+// the same for up to kMaxSplitSrc sources in one launch (blockIdx.z = source): all layers of an LSTM stack at once
+constexpr int kMaxSplitSrc = 8;
+struct SplitMulti {
+    const float *src[kMaxSplitSrc]; long long src_pitch[kMaxSplitSrc]; int w[kMaxSplitSrc];
+    __nv_bfloat16 *dst[kMaxSplitSrc]; long long dst_pitch[kMaxSplitSrc]; int K[kMaxSplitSrc], off[kMaxSplitSrc];
+    const long long *idx; int n;
+};
+
+__global__ void __launch_bounds__(256)
+lstm_split_rows_multi_kernel(const SplitMulti p)
+{
+    const int z = blockIdx.z, r = blockIdx.y;
+    const long long row = p.idx ? p.idx[r] : r;
+    const float *s = p.src[z] + row * p.src_pitch[z];
+    __nv_bfloat16 *d = p.dst[z] + (long long)r * p.dst_pitch[z] + p.off[z];
+    const int w = p.w[z], K = p.K[z];
+    for (int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4; c < w; c += gridDim.x * blockDim.x * 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(s + c));
+        Bf16x4 p0, p1, p2;
+        split3(v.x, p0.v[0], p1.v[0], p2.v[0]);
+        split3(v.y, p0.v[1], p1.v[1], p2.v[1]);
+        split3(v.z, p0.v[2], p1.v[2], p2.v[2]);
+        split3(v.w, p0.v[3], p1.v[3], p2.v[3]);
+        *reinterpret_cast<Bf16x4 *>(d + c) = p0;
+        *reinterpret_cast<Bf16x4 *>(d + K + c) = p1;
+        *reinterpret_cast<Bf16x4 *>(d + 2 * K + c) = p2;
+    }
+}
+
 __device__ __forceinline__ float sigmoid_f32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
 struct CellParams {
@@ -174,6 +203,44 @@ extern "C" int e2e_lstm_split_rows(const float *src, long long src_pitch, const 
         count_launch();
     }
     return check_launch("e2e_lstm_split_rows");
+}
+
+extern "C" int e2e_lstm_split_rows_multi(int n_src, const float *const *srcs, const long long *src_pitches, const int *widths,
+                                         void *const *dsts_bf16, const long long *dst_pitches, const int *Ks, const int *offs,
+                                         const long long *row_idx, int n, void *stream)
+{
+    using namespace e2e;
+    if (!srcs || !src_pitches || !widths || !dsts_bf16 || !dst_pitches || !Ks || !offs)
+        return set_error(E2E_ERR_ARG, "e2e_lstm_split_rows_multi: null pointer");
+    if (n_src <= 0 || n_src > kMaxSplitSrc || n <= 0) return set_error(E2E_ERR_ARG, "e2e_lstm_split_rows_multi: bad size");
+    SplitMulti p;
+    int wmax = 0;
+    for (int i = 0; i < n_src; ++i) {
+        if (!srcs[i] || !dsts_bf16[i]) return set_error(E2E_ERR_ARG, "e2e_lstm_split_rows_multi: null pointer");
+        const bool vec = (widths[i] % 4 == 0) && (src_pitches[i] % 4 == 0) && (dst_pitches[i] % 4 == 0) && (Ks[i] % 4 == 0) &&
+                         (offs[i] % 4 == 0) && !(reinterpret_cast<uintptr_t>(srcs[i]) & 15) && !(reinterpret_cast<uintptr_t>(dsts_bf16[i]) & 7);
+        if (!vec) return set_error(E2E_ERR_UNSUPPORTED, "e2e_lstm_split_rows_multi: source %d is not 16-byte vectorisable", i);
+        if (widths[i] <= 0 || offs[i] < 0 || offs[i] + widths[i] > Ks[i] || dst_pitches[i] < 3LL * Ks[i] || src_pitches[i] < widths[i])
+            return set_error(E2E_ERR_ARG, "e2e_lstm_split_rows_multi: bad geometry of source %d", i);
+        p.src[i] = srcs[i]; p.src_pitch[i] = src_pitches[i]; p.w[i] = widths[i];
+        p.dst[i] = static_cast<__nv_bfloat16 *>(dsts_bf16[i]); p.dst_pitch[i] = dst_pitches[i]; p.K[i] = Ks[i]; p.off[i] = offs[i];
+        wmax = widths[i] > wmax ? widths[i] : wmax;
+    }
+    const int bx = (wmax + 1023) / 1024;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int r0 = 0; r0 < n; r0 += 65535) {
+        const int rows = n - r0 < 65535 ? n - r0 : 65535;
+        SplitMulti q = p;
+        q.n = rows;
+        q.idx = row_idx ? row_idx + r0 : nullptr;
+        for (int i = 0; i < n_src; ++i) {
+            if (!row_idx) q.src[i] = p.src[i] + (long long)r0 * p.src_pitch[i];
+            q.dst[i] = p.dst[i] + (long long)r0 * p.dst_pitch[i];
+        }
+        lstm_split_rows_multi_kernel<<<dim3(bx, rows, n_src), 256, 0, st>>>(q);
+        count_launch();
+    }
+    return check_launch("e2e_lstm_split_rows_multi");
 }
 
 extern "C" int e2e_lstm_cell(const float *gates, long long gates_pitch, const float *bias, const float *table, const long long *tok,

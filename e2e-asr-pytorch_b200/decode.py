@@ -215,7 +215,7 @@ class BeamDecoder(nn.Module):
             mark("ctc_posterior")
             for step in range(n_steps):                                            # decode.py:104
                 k = n_run[step]
-                att_logits, lm_logits = stepper.step(buf.last_tok[:k].reshape(-1).long(), k)
+                att_logits, lm_logits = stepper.step(buf.last_tok64[:k].view(-1), k)
                 mark("step_rest")
                 ops.beam_candidates(att_logits, k, beam, vocab, n_cand, buf.n_active, buf.att_stats, buf.cand)
                 if self.apply_ctc:
@@ -235,7 +235,7 @@ class BeamDecoder(nn.Module):
                     r_prev = r_cur
                 ops.beam_combine_prune(buf, att_logits, lm_logits, vocab, step, ctc_w, lm_w, EOS_THRESHOLD, n_run=k)
                 mark("beam_kernels")
-                stepper.reorder(buf.parent_slot)
+                stepper.reorder(buf.parent_row)
                 mark("reorder")
 
             tok, sc, ln, avg, n = ops.beam_finalize(buf)

@@ -111,6 +111,8 @@ class BeamBuffers:
         self.last_tok, self.prefix_len, self.prev_lane = z(u, b), z(u, b), z(u, b)
         self.score_sum, self.ctc_prob = z(u, b, dt=F32), z(u, b, dt=F32)
         self.parent_slot = z(u, b)
+        self.parent_row = torch.arange(u * b, dtype=torch.int64, device=device).view(u, b)     # u*B + parent slot
+        self.last_tok64 = z(u, b, dt=torch.int64)
         self.hist_tok, self.hist_parent = z(self.S, u, b), z(self.S, u, b)
         self.hist_score = z(self.S, u, b, dt=F32)
         self.fin_cap = int(fin_cap if fin_cap is not None else b)      # best-B closed hypotheses suffice
@@ -140,7 +142,7 @@ def beam_combine_prune(buf, att_logits, lm_logits, vocab, step, ctc_weight, lm_w
         L.ptr(buf.parent_slot),
         L.ptr(buf.hist_tok), L.ptr(buf.hist_parent), L.ptr(buf.hist_score),
         L.ptr(buf.fin_count), L.ptr(buf.fin_step), L.ptr(buf.fin_parent), L.ptr(buf.fin_sum), L.ptr(buf.fin_score),
-        buf.fin_cap, L.ptr(buf.status), int(n_run), _stream()))
+        buf.fin_cap, L.ptr(buf.status), int(n_run), L.ptr(buf.parent_row), L.ptr(buf.last_tok64), _stream()))
 
 
 def beam_finalize(buf, out_cap=None):
@@ -219,6 +221,34 @@ def lstm_split_rows(src, row_idx, n, dst, k, off):
         raise ValueError("lstm_split_rows: src has fewer than n rows")
     L.check(L.load().e2e_lstm_split_rows(L.ptr(src), int(src.stride(0)), L.ptr(row_idx), int(n), int(w),
                                         L.ptr(dst), int(dst.stride(0)), int(k), int(off), _stream()))
+
+
+class SplitPlan:
+    """Pre-marshalled argument arrays of e2e_lstm_split_rows_multi for a fixed set of (src, dst, K, off) pairs:
+    the per-step call then costs one ctypes dispatch."""
+
+    def __init__(self, pairs):
+        import ctypes
+        n = len(pairs)
+        for src, dst, k, off in pairs:
+            _chk(src, F32, "src")
+            _chk(dst, torch.bfloat16, "dst")
+        self.keep = pairs
+        self.n = n
+        self.srcs = (ctypes.c_void_p * n)(*[p[0].data_ptr() for p in pairs])
+        self.src_pitch = (ctypes.c_longlong * n)(*[int(p[0].stride(0)) for p in pairs])
+        self.widths = (ctypes.c_int * n)(*[int(p[0].shape[1]) for p in pairs])
+        self.dsts = (ctypes.c_void_p * n)(*[p[1].data_ptr() for p in pairs])
+        self.dst_pitch = (ctypes.c_longlong * n)(*[int(p[1].stride(0)) for p in pairs])
+        self.ks = (ctypes.c_int * n)(*[int(p[2]) for p in pairs])
+        self.offs = (ctypes.c_int * n)(*[int(p[3]) for p in pairs])
+        self.rows = min(min(p[0].shape[0], p[1].shape[0]) for p in pairs)
+
+    def run(self, row_idx, n_rows):
+        if n_rows > self.rows or (row_idx is not None and (row_idx.dtype != torch.int64 or not row_idx.is_cuda or row_idx.numel() < n_rows)):
+            raise ValueError("SplitPlan.run: bad row index / row count")
+        L.check(L.load().e2e_lstm_split_rows_multi(self.n, self.srcs, self.src_pitch, self.widths, self.dsts, self.dst_pitch,
+                                                  self.ks, self.offs, L.ptr(row_idx), int(n_rows), _stream()))
 
 
 def lstm_cell(gates, bias, c_prev, row_idx, n, c_new, h_new, table=None, tok=None, a_next=None, k_next=0, off_next=0):

@@ -172,6 +172,10 @@ class _FusedLstm:
         self.gates = torch.empty(n, 4 * d, device=device)          # GEMM accumulator, reused by every layer
         self.idx = torch.arange(n, device=device)
         self.cur = 0
+        from . import ops
+        vec = d % 4 == 0 and all(k % 4 == 0 for k in self.k_in)
+        self.plans = [ops.SplitPlan([(self.h[c][l], self.a[l], self.k_in[l] + d, self.k_in[l]) for l in range(self.layers)])
+                      if (vec and self.layers <= 8) else None for c in range(2)]
 
     def hidden(self, n):
         """[n, layers*D] hidden states of the rows' parents (what Decoder.get_query reads, asr.py:251-254)."""
@@ -183,8 +187,11 @@ class _FusedLstm:
         from . import ops
         cur, new, d = self.cur, 1 - self.cur, self.dim
         idx = self.idx
-        for l in range(self.layers):                                   # recurrent halves of the A operands
-            ops.lstm_split_rows(self.h[cur][l], idx, n, self.a[l], self.k_in[l] + d, self.k_in[l])
+        if self.plans[cur] is not None:                                # recurrent halves of all A operands, one launch
+            self.plans[cur].run(idx, n)
+        else:
+            for l in range(self.layers):
+                ops.lstm_split_rows(self.h[cur][l], idx, n, self.a[l], self.k_in[l] + d, self.k_in[l])
         if self.k_in[0] > 0:
             ops.lstm_split_rows(x0.contiguous(), None, n, self.a[0], self.k_in[0] + d, 0)
         for l in range(self.layers):
@@ -308,7 +315,6 @@ class BatchedStepper:
             self.lm_rnn.start(self.N, dev)
         else:
             self.lm_state = self.lm_rnn.zeros(self.N, dev) if self.lm_rnn is not None else None
-        self._base = torch.arange(u, device=dev, dtype=torch.long)[:, None] * beam
         self._enc_len32 = enc_len.to(torch.int32).contiguous()
 
     # -- once per decode step ---------------------------------------------------------------
@@ -361,12 +367,12 @@ class BatchedStepper:
             self.mark("step_lm")
         return att_logits.contiguous(), (lm_logits.contiguous() if lm_logits is not None else None)
 
-    def reorder(self, parent_slot):
-        """parent_slot [U,B] int32 (slot of each survivor's parent): children inherit the
-        post-step states of their parent (decode.py:159-162,250-257).  Only the rows of the
-        utterances advanced by the last :meth:`step` are touched."""
+    def reorder(self, parent_row):
+        """parent_row [U,B] int64 (row u*B + slot of each survivor's parent, written by e2e_beam_combine_prune):
+        children inherit the post-step states of their parent (decode.py:159-162,250-257).  Only the rows of
+        the utterances advanced by the last :meth:`step` are touched."""
         k = self._k
-        idx = (self._base[:k] + parent_slot[:k].long()).reshape(-1)
+        idx = parent_row[:k].view(-1)
         if self.dec_fused:
             self.dec.reorder(idx)
         else:

@@ -135,6 +135,8 @@ int e2e_beam_candidates(const float *att_logits, int ld, int U, int B, int V, in
  *   fin_count [U]; fin_step, fin_parent (int32), fin_sum, fin_score (fp32): [U][fin_cap]
  * Utterances with step >= max_len[u] are left untouched; only utterances 0..n_run-1 are visited
  * (<= 0: all U).
+ *   parent_row, last_tok64 [U][B] int64 (either may be NULL): u*B + parent_slot and last_tok again, in the
+ *   index type the caller's state gathers / embedding look-ups take, so that no conversion kernels are needed.
  *   lm_logits may be NULL iff E2E_BEAM_USE_LM is clear; cand/psi iff E2E_BEAM_USE_CTC is clear. */
 int e2e_beam_combine_prune(const float *att_logits, int ld_att, const float *att_stats,
                            const float *lm_logits, int ld_lm,
@@ -147,7 +149,8 @@ int e2e_beam_combine_prune(const float *att_logits, int ld_att, const float *att
                            int *parent_slot,
                            int *hist_tok, int *hist_parent, float *hist_score,
                            int *fin_count, int *fin_step, int *fin_parent, float *fin_sum, float *fin_score,
-                           int fin_cap, int *status, int n_run, void *stream);
+                           int fin_cap, int *status, int n_run,
+                           long long *parent_row, long long *last_tok64, void *stream);
 
 /* Final N-best selection + back-tracking.  Replaces src/decode.py:180-183 and
  * Hypothesis.outIndex (src/decode.py:279-281): closed hypotheses followed by the last
@@ -204,6 +207,13 @@ int e2e_attention_loc_full(const float *key_t, const float *value, const float *
  *   src fp32 [*][src_pitch]; dst bf16 [n][dst_pitch], dst_pitch >= 3*K: the A operand [a1 | a2 | a3] of the GEMMs. */
 int e2e_lstm_split_rows(const float *src, long long src_pitch, const long long *row_idx, int n, int w,
                         void *dst_bf16, long long dst_pitch, int K, int off, void *stream);
+
+/* e2e_lstm_split_rows for up to 8 (source, destination) pairs in ONE launch — the recurrent halves of all layers of an
+ * LSTM stack.  The arrays are HOST arrays of n_src entries (device pointers / sizes); every source must be 16-byte
+ * vectorisable (width, pitches, K, off multiples of 4). */
+int e2e_lstm_split_rows_multi(int n_src, const float *const *srcs_host, const long long *src_pitches_host, const int *widths_host,
+                              void *const *dsts_bf16_host, const long long *dst_pitches_host, const int *Ks_host, const int *offs_host,
+                              const long long *row_idx, int n, void *stream);
 
 /* e2e_lstm_cell: z = gates[r] + bias (+ table[tok[r]]), gate order i,f,g,o (torch.nn.LSTM);
  *   c'[r] = sigmoid(z_f) * c_prev[row(r)] + sigmoid(z_i) * tanh(z_g);  h'[r] = sigmoid(z_o) * tanh(c'[r])

@@ -48,7 +48,7 @@ def test_batched_stepper_matches_per_hypothesis_modules():
         enc, enc_len = st.encode(feat, fl)
         st.start(enc, enc_len, beam)
         a1, l1 = st.step(torch.zeros(len(lens) * beam, dtype=torch.long))
-        st.reorder(torch.zeros((len(lens), beam), dtype=torch.int32))
+        st.reorder((torch.arange(len(lens))[:, None] * beam).expand(len(lens), beam).contiguous())     # every child from slot 0
         toks = [5, 7, 9]
         a2, l2 = st.step(torch.tensor(toks * len(lens)))
         for u, n in enumerate(lens):
