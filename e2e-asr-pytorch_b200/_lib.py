@@ -87,9 +87,11 @@ def load():
     """Load (building first if needed) the shared object; never falls back."""
     global _lib
     if _lib is None:
-        path = _build.LIB_PATH
-        if _build.stale():
-            path = _build.build()
+        path = os.environ.get("E2E_ASR_B200_LIB")          # tuning builds (tools/): an explicit library, never a fallback
+        if not path:
+            path = _build.LIB_PATH
+            if _build.stale():
+                path = _build.build()
         lib = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError if a declared symbol is missing

@@ -36,8 +36,17 @@
 
 namespace e2e {
 
-constexpr int kTile = 32;            // frames per shared-memory tile
-constexpr int kPhiPitch = 2 * kTile + 2; // floats per phi row: 32 x (sum, blank) + pad (bank spread across hypotheses)
+#ifndef E2E_PS_MINBLOCKS
+#define E2E_PS_MINBLOCKS 6           // register cap 85: measured 19 % faster than a cap of 64 (tools/sweep_prefix_variants.py)
+#endif
+#ifndef E2E_PS_UNROLL
+#define E2E_PS_UNROLL 4
+#endif
+// Frames per shared-memory tile (template parameter kT of the kernel): 16 for machine-filling launches (smaller
+// tiles -> less shared memory -> more resident CTAs: 0.149 vs 0.162 ms on the 2620-utterance launch), 32 for
+// small ones, whose duration is one utterance's chain and which pay per tile (0.083 vs 0.095 ms on 64 x 825 frames).
+constexpr int kTileBig = 16, kTileSmall = 32;
+__host__ __device__ constexpr int phi_pitch(int tile) { return 2 * tile + 2; }   // floats per phi row: tile x (sum, blank) + pad
 constexpr int kMaxRowFloats = 256;   // rows variant up to 1 KB per posterior row
 constexpr int kMaxLanes = 128;       // lanes (= threads) per CTA
 constexpr int kLutBytes = kLutNodes * kLutCopies * 16;
@@ -54,14 +63,14 @@ struct PrefixParams {
     int hyps_per_cta;     // rows of the phi tile
 };
 
-__host__ __device__ inline size_t prefix_xs_bytes(bool gather, int lanes, int Vp)
+__host__ __device__ inline size_t prefix_xs_bytes(bool gather, int lanes, int Vp, int tile)
 {
-    // rows: two tiles of kTile posterior rows.  gather: two tiles of per-lane columns + the blank column.
-    size_t f = gather ? (size_t)2 * (kTile * lanes + kTile) : (size_t)2 * kTile * Vp;
-    return ((f + 3) & ~(size_t)3) * 4;
+    // rows: two tiles of posterior rows.  gather: two tiles of per-lane columns + the blank column.
+    size_t f = gather ? (size_t)2 * (tile * lanes + tile) : (size_t)2 * tile * Vp;
+    return ((f + 31) & ~(size_t)31) * 4;          // 128-byte multiples: TMA destinations stay aligned
 }
-__host__ __device__ inline size_t prefix_phis_bytes(int H) { return (size_t)2 * H * kPhiPitch * 4; }
-__host__ __device__ inline size_t prefix_stage_bytes(int H) { return (size_t)H * kTile * 8; }   // raw parent states of one tile
+__host__ __device__ inline size_t prefix_phis_bytes(int H, int tile) { return (size_t)2 * H * phi_pitch(tile) * 4; }
+__host__ __device__ inline size_t prefix_stage_bytes(int H, int tile) { return (size_t)H * tile * 8; }   // raw parent states of one tile
 
 // kVp / kLU: compile-time copies of Vp and B*C for the shapes the beam search runs all day
 // (0 = take them from the parameters): per-frame offsets then become instruction immediates.
@@ -81,11 +90,12 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
-template <bool kGather, int kMath, int kVp, int kLU, bool kTmap>
-__global__ void __launch_bounds__(kMaxLanes, 8)
+template <bool kGather, int kMath, int kVp, int kLU, bool kTmap, int kT>
+__global__ void __launch_bounds__(kMaxLanes, E2E_PS_MINBLOCKS)
 prefix_score_kernel(const PrefixParams p, const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int kPhiP = phi_pitch(kT);
     const int tid = threadIdx.x, nt = blockDim.x;
     const int nl = nt;
     const int lt = tid;                           // lane index within the CTA
@@ -104,9 +114,9 @@ prefix_score_kernel(const PrefixParams p, const __grid_constant__ CUtensorMap tm
     // ---- shared memory: LUT replicas | x tiles | phi tiles (x2) | raw parent states | s_plane[H] | s_red[2] | mbarriers[2]
     const int H = p.hyps_per_cta;
     const size_t xs_off = kLutBytes;
-    const size_t phis_off = xs_off + prefix_xs_bytes(kGather, nl, Vp);
-    const size_t stage_off = phis_off + prefix_phis_bytes(H);
-    const size_t misc_off = stage_off + prefix_stage_bytes(H);
+    const size_t phis_off = xs_off + prefix_xs_bytes(kGather, nl, Vp, kT);
+    const size_t stage_off = phis_off + prefix_phis_bytes(H, kT);
+    const size_t misc_off = stage_off + prefix_stage_bytes(H, kT);
     const size_t bars_off = (misc_off + (size_t)(H + 2) * 4 + 7) & ~(size_t)7;
     float4 *lut_base = reinterpret_cast<float4 *>(smem_raw);
     float *xs = reinterpret_cast<float *>(smem_raw + xs_off);
@@ -116,7 +126,7 @@ prefix_score_kernel(const PrefixParams p, const __grid_constant__ CUtensorMap tm
     int *s_red = s_plane + H;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + bars_off);
     const uint32_t lut = softplus_lut_adj(lut_base + (tid & (kLutCopies - 1)));   // this thread's replica
-    const int g_tile = kTile * nl + kTile;                        // gather variant: floats per x tile
+    const int g_tile = kT * nl + kT;                        // gather variant: floats per x tile
 
     // ---- per-lane setup -----------------------------------------------------------------------
     const int lane_u = lane0 + lt;                // lane within the utterance
@@ -163,38 +173,38 @@ prefix_score_kernel(const PrefixParams p, const __grid_constant__ CUtensorMap tm
     float psi = nb;                                            // psi = r[start-1, 0, :] (src/ctc.py:85)
 
     if (cta_start != 0x7fffffff) {
-        const int first_tile = cta_start / kTile;
-        const int n_tiles = (T + kTile - 1) / kTile;
+        const int first_tile = cta_start / kT;
+        const int n_tiles = (T + kT - 1) / kT;
         // rows below the first computed tile are log-zero by construction
         if (run && fill_dead)
-            for (int t = 0; t < first_tile * kTile && t < T; ++t) rout[(long long)t * LU] = dead;
+            for (int t = 0; t < first_tile * kT && t < T; ++t) rout[(long long)t * LU] = dead;
 
         auto issue_rows = [&](int k) {   // warp 0 brings posterior tile k into its ring stage
-            const int t0 = k * kTile;
+            const int t0 = k * kT;
             uint64_t *bar = &bars[k & 1];
-            float *dst = xs + (size_t)(k & 1) * kTile * Vp;
+            float *dst = xs + (size_t)(k & 1) * kT * Vp;
             if (kTmap) {
                 // one box copy; frames beyond Tmax are zero filled by the TMA unit and still count as bytes
                 if (tid == 0) {
-                    mbar_arrive_expect_tx(bar, (uint32_t)kTile * Vp * 4u);
+                    mbar_arrive_expect_tx(bar, (uint32_t)kT * Vp * 4u);
                     tma_load_tile(dst, &tmap, u, t0, bar);
                 }
             } else {
-                const int rows = min(kTile, T - t0);
+                const int rows = min(kT, T - t0);
                 if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)rows * Vp * 4u);
                 __syncwarp();
                 if (tid < rows)
                     bulk_g2s(dst + (size_t)tid * Vp, p.x + (long long)(t0 + tid) * xstride + xrow0, (uint32_t)Vp * 4u, bar);
             }
         };
-        // phi tile k, entry (hl, tt) describes r_prev at frame k*kTile + tt - 1.  Entry i of a tile is
+        // phi tile k, entry (hl, tt) describes r_prev at frame k*kT + tt - 1.  Entry i of a tile is
         // fetched (phi_fetch) and converted (phi_convert) by the same thread, so cp.async.wait_all is
         // all the ordering the staging buffer needs.
-        const int n_phi = H * kTile;
+        const int n_phi = H * kT;
         auto phi_fetch = [&](int k) {
             for (int i = tid; i < n_phi; i += nt) {
-                const int hl = i / kTile, tt = i - hl * kTile;
-                const int ts = k * kTile + tt - 1;
+                const int hl = i / kT, tt = i - hl * kT;
+                const int ts = k * kT + tt - 1;
                 const int pl = s_plane[hl];
                 if (pl >= 0 && ts >= 0 && ts < T) cp_async_8(stage_buf + i, rprev_u + (long long)ts * p.lanes_prev + pl);
                 else stage_buf[i] = dead;
@@ -203,12 +213,12 @@ prefix_score_kernel(const PrefixParams p, const __grid_constant__ CUtensorMap tm
         auto phi_convert = [&](int k) {
             cp_async_wait_all();
             for (int i = tid; i < n_phi; i += nt) {
-                const int hl = i / kTile, tt = i - hl * kTile;
+                const int hl = i / kT, tt = i - hl * kT;
                 const float2 a = stage_buf[i];
                 float2 ph;
                 ph.x = logaddexp<kMath>(a.x, a.y, lut);
                 ph.y = full ? logaddexp<kMath>(E2E_CTC_LOGZERO, a.y, lut) : a.y;
-                *reinterpret_cast<float2 *>(phis + (size_t)(k & 1) * H * kPhiPitch + hl * kPhiPitch + 2 * tt) = ph;
+                *reinterpret_cast<float2 *>(phis + (size_t)(k & 1) * H * kPhiP + hl * kPhiP + 2 * tt) = ph;
             }
         };
 
@@ -222,11 +232,11 @@ prefix_score_kernel(const PrefixParams p, const __grid_constant__ CUtensorMap tm
         }
 
         // this thread's column inside a phi row (sum or blank-only variant)
-        const int phi_col = (h - h_lo) * kPhiPitch + (special ? 1 : 0);
+        const int phi_col = (h - h_lo) * kPhiP + (special ? 1 : 0);
         uint32_t parity = 0u;                                  // bit s = phase of mbarrier s
         for (int k = first_tile; k < n_tiles; ++k) {
-            const int t0 = k * kTile;
-            const int rows = min(kTile, T - t0);
+            const int t0 = k * kT;
+            const int rows = min(kT, T - t0);
             if (k + 1 < n_tiles) phi_fetch(k + 1);             // in flight while tile k is computed
             const float *xcp, *xbp;   // this thread's candidate column / the blank column of tile row 0
             if (kGather) {
@@ -236,12 +246,12 @@ prefix_score_kernel(const PrefixParams p, const __grid_constant__ CUtensorMap tm
                     for (int tt = 0; tt < rows; ++tt)
                         xg[tt * nl + lt] = __ldg(p.x + (long long)(t0 + tt) * xstride + xrow0 + tok);
                 }
-                if (tid < rows) xg[kTile * nl + tid] = __ldg(p.x + (long long)(t0 + tid) * xstride + xrow0 + E2E_CTC_BLANK);
-                xcp = xg + lt; xbp = xg + kTile * nl;
+                if (tid < rows) xg[kT * nl + tid] = __ldg(p.x + (long long)(t0 + tid) * xstride + xrow0 + E2E_CTC_BLANK);
+                xcp = xg + lt; xbp = xg + kT * nl;
             } else {
                 mbar_wait(&bars[k & 1], (parity >> (k & 1)) & 1u);
                 parity ^= 1u << (k & 1);
-                const float *xt = xs + (size_t)(k & 1) * kTile * Vp;
+                const float *xt = xs + (size_t)(k & 1) * kT * Vp;
                 xcp = xt + tok; xbp = xt + E2E_CTC_BLANK;
             }
             const int xc_step = kGather ? nl : Vp, xb_step = kGather ? 1 : Vp;
@@ -260,7 +270,7 @@ prefix_score_kernel(const PrefixParams p, const __grid_constant__ CUtensorMap tm
                             if (!(t0 + tt == 0 && plen == 0)) rout[(long long)(t0 + tt) * LU] = dead;
                     tt = stop;
                 }
-                const float *php = phis + (size_t)(k & 1) * H * kPhiPitch + phi_col + 2 * tt;
+                const float *php = phis + (size_t)(k & 1) * H * kPhiP + phi_col + 2 * tt;
                 xcp += tt * xc_step; xbp += tt * xb_step;
                 float2 *outp = rout + (long long)(t0 + tt) * LU;
                 // 3 LDS, 3 log-add-exp, 1 STG.64 per frame
@@ -274,9 +284,11 @@ prefix_score_kernel(const PrefixParams p, const __grid_constant__ CUtensorMap tm
                     nb = nnb; bl = nbl;
                     outp[(long long)q * LU] = make_float2(nnb, nbl);
                 };
-                for (; tt + 4 <= rows; tt += 4) {
-                    frame(0); frame(1); frame(2); frame(3);
-                    php += 8; xcp += 4 * xc_step; xbp += 4 * xb_step; outp += 4LL * LU;
+                for (; tt + E2E_PS_UNROLL <= rows; tt += E2E_PS_UNROLL) {
+#pragma unroll
+                    for (int q = 0; q < E2E_PS_UNROLL; ++q) frame(q);
+                    php += 2 * E2E_PS_UNROLL; xcp += E2E_PS_UNROLL * xc_step; xbp += E2E_PS_UNROLL * xb_step;
+                    outp += (long long)E2E_PS_UNROLL * LU;
                 }
                 for (; tt < rows; ++tt) {
                     frame(0);
@@ -301,9 +313,9 @@ prefix_score_kernel(const PrefixParams p, const __grid_constant__ CUtensorMap tm
     }
 }
 
-static size_t prefix_smem_bytes(bool gather, int lanes, int Vp, int H)
+static size_t prefix_smem_bytes(bool gather, int lanes, int Vp, int H, int tile)
 {
-    size_t b = kLutBytes + prefix_xs_bytes(gather, lanes, Vp) + prefix_phis_bytes(H) + prefix_stage_bytes(H);
+    size_t b = kLutBytes + prefix_xs_bytes(gather, lanes, Vp, tile) + prefix_phis_bytes(H, tile) + prefix_stage_bytes(H, tile);
     b = ((b + (size_t)(H + 2) * 4 + 7) & ~(size_t)7) + 16;
     return (b + 15) & ~(size_t)15;
 }
@@ -330,14 +342,14 @@ static EncodeTiledFn tensor_map_encoder()
     return fn;
 }
 
-// Tensor map of the posterior tensor x [Tmax][U][Vp] (fp32) with a (Vp, 1, kTile) box.
-static int make_posterior_map(CUtensorMap *map, const float *x, int Tmax, int U, int Vp)
+// Tensor map of the posterior tensor x [Tmax][U][Vp] (fp32) with a (Vp, 1, tile) box.
+static int make_posterior_map(CUtensorMap *map, const float *x, int Tmax, int U, int Vp, int tile)
 {
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return set_error(E2E_ERR_LAUNCH, "e2e_ctc_prefix_score: cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[3] = {(cuuint64_t)Vp, (cuuint64_t)U, (cuuint64_t)Tmax};
     const cuuint64_t strides[2] = {(cuuint64_t)Vp * 4, (cuuint64_t)U * Vp * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)Vp, 1u, (cuuint32_t)kTile};
+    const cuuint32_t box[3] = {(cuuint32_t)Vp, 1u, (cuuint32_t)tile};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(x), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -396,27 +408,35 @@ extern "C" int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int
 
     const bool gather = Vp > kMaxRowFloats;
     const int math = (flags & E2E_PREFIX_FAST_MATH) ? kMathMufu : ((flags & E2E_PREFIX_LIBM_MATH) ? kMathLibm : kMathLut);
-    const size_t smem = prefix_smem_bytes(gather, nl, Vp, p.hyps_per_cta);
     const bool fixed = !gather && Vp == 32 && LU == 96;      // char vocabulary, beam 8 (BASELINE cfg2)
     const bool use_map = !gather && !(flags & E2E_PREFIX_ROW_COPIES);
+    // Tile size by launch size (only the default-math tensor-map kernels are built with the small tile)
+    static const long long small_tile_from = []() {
+        const char *e = getenv("E2E_PREFIX_SMALL_TILE_FROM");    // tuning knob: CTAs from which the 16-frame tile is used
+        return e ? atoll(e) : 1000LL;
+    }();
+    const bool big_launch = use_map && math == kMathLut && grid >= small_tile_from;
+    const int tile = big_launch ? kTileBig : kTileSmall;
+    const size_t smem = prefix_smem_bytes(gather, nl, Vp, p.hyps_per_cta, tile);
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
     if (use_map) {
-        const int rc = make_posterior_map(&map, x, Tmax, U, Vp);
+        const int rc = make_posterior_map(&map, x, Tmax, U, Vp, tile);
         if (rc != E2E_OK) return rc;
     }
+    constexpr int TS = kTileSmall, TB = kTileBig;
     PrefixKernel kern;
     if (gather)
-        kern = math == kMathLut ? prefix_score_kernel<true, kMathLut, 0, 0, false>
-                                : (math == kMathMufu ? prefix_score_kernel<true, kMathMufu, 0, 0, false> : prefix_score_kernel<true, kMathLibm, 0, 0, false>);
+        kern = math == kMathLut ? prefix_score_kernel<true, kMathLut, 0, 0, false, TS>
+                                : (math == kMathMufu ? prefix_score_kernel<true, kMathMufu, 0, 0, false, TS> : prefix_score_kernel<true, kMathLibm, 0, 0, false, TS>);
     else if (!use_map)
-        kern = math == kMathLut ? prefix_score_kernel<false, kMathLut, 0, 0, false>
-                                : (math == kMathMufu ? prefix_score_kernel<false, kMathMufu, 0, 0, false> : prefix_score_kernel<false, kMathLibm, 0, 0, false>);
-    else if (fixed && math == kMathLut)
-        kern = prefix_score_kernel<false, kMathLut, 32, 96, true>;
-    else
-        kern = math == kMathLut ? prefix_score_kernel<false, kMathLut, 0, 0, true>
-                                : (math == kMathMufu ? prefix_score_kernel<false, kMathMufu, 0, 0, true> : prefix_score_kernel<false, kMathLibm, 0, 0, true>);
+        kern = math == kMathLut ? prefix_score_kernel<false, kMathLut, 0, 0, false, TS>
+                                : (math == kMathMufu ? prefix_score_kernel<false, kMathMufu, 0, 0, false, TS> : prefix_score_kernel<false, kMathLibm, 0, 0, false, TS>);
+    else if (math == kMathLut) {
+        if (fixed) kern = big_launch ? prefix_score_kernel<false, kMathLut, 32, 96, true, TB> : prefix_score_kernel<false, kMathLut, 32, 96, true, TS>;
+        else kern = big_launch ? prefix_score_kernel<false, kMathLut, 0, 0, true, TB> : prefix_score_kernel<false, kMathLut, 0, 0, true, TS>;
+    } else
+        kern = math == kMathMufu ? prefix_score_kernel<false, kMathMufu, 0, 0, true, TS> : prefix_score_kernel<false, kMathLibm, 0, 0, true, TS>;
     if (smem > 48 * 1024) {
         if (smem > 200 * 1024) return set_error(E2E_ERR_UNSUPPORTED, "e2e_ctc_prefix_score: %zu bytes of shared memory needed", smem);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,0 +1,16 @@
+"""Run the prefix-score micro-benchmark against tuning builds of the library (lib/variants/lib_<name>.so, built with
+-DE2E_PS_MINBLOCKS / -DE2E_PS_UNROLL / -DE2E_PS_TILE) and print ms per launch for three launch shapes."""
+import glob, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+shapes = [["--utts", "2620"], ["--utts", "2620", "--plen", "60", "--skip-dead", "1"], ["--utts", "64", "--frames", "825"],
+          ["--utts", "600", "--frames", "400", "--ragged", "1", "--plen", "100", "--skip-dead", "1"]]
+for lib in sorted(glob.glob(os.path.join(ROOT, "e2e-asr-pytorch_b200", "lib", "variants", "lib_*.so"))):
+    env = dict(os.environ, E2E_ASR_B200_LIB=lib)
+    ms = []
+    for sh in shapes:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_prefix.py")] + sh, capture_output=True, text=True, env=env)
+        try:
+            ms.append(round(json.loads(out.stdout.strip().split("\n")[-1])["ms_mean"], 4))
+        except Exception:
+            ms.append(None)
+    print(os.path.basename(lib), ms, flush=True)
