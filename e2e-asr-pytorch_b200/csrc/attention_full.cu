@@ -53,8 +53,11 @@ struct AttFullParams {
 
 // shared memory (floats): wc [W][KP] | cst [A][16] (loc_proj row 0..11, gen_energy weight at 12) |
 //                         q [A][Bq] | pa [warps][NB][32 + W - 1]
+#ifndef E2E_AF_MINBLOCKS
+#define E2E_AF_MINBLOCKS 3
+#endif
 template <int NB, int KP>
-__global__ void __launch_bounds__(kAfThreads, 3)
+__global__ void __launch_bounds__(kAfThreads, E2E_AF_MINBLOCKS)
 attention_energy_kernel(const AttFullParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

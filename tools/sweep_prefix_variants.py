@@ -4,13 +4,17 @@ import glob, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 shapes = [["--utts", "2620"], ["--utts", "2620", "--plen", "60", "--skip-dead", "1"], ["--utts", "64", "--frames", "825"],
           ["--utts", "600", "--frames", "400", "--ragged", "1", "--plen", "100", "--skip-dead", "1"]]
+if len(sys.argv) > 1 and sys.argv[1] == "attention":
+    tool, shapes = "bench_attention.py", [["--ragged", "1"], ["--utts", "2620", "--frames", "824", "--ragged", "1"], ["--utts", "100", "--frames", "824", "--ragged", "1"]]
+else:
+    tool = "bench_prefix.py"
 for lib in sorted(glob.glob(os.path.join(ROOT, "e2e-asr-pytorch_b200", "lib", "variants", "lib_*.so"))):
     env = dict(os.environ, E2E_ASR_B200_LIB=lib)
     ms = []
     for sh in shapes:
-        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_prefix.py")] + sh, capture_output=True, text=True, env=env)
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool)] + sh, capture_output=True, text=True, env=env)
         try:
-            ms.append(round(json.loads(out.stdout.strip().split("\n")[-1])["ms_mean"], 4))
+            ms.append(round((lambda d: d.get("ms_mean", d.get("ms")))(json.loads(out.stdout.strip().split("\n")[-1])), 4))
         except Exception:
             ms.append(None)
     print(os.path.basename(lib), ms, flush=True)
