@@ -146,3 +146,16 @@ def test_sharded_decode_allgather_gloo_world2(tmp_path):
         got = torch.load(str(tmp_path / ("rank%d.pt" % r)))
         for a, b in zip(got, want):
             assert torch.equal(a, b)
+
+
+def test_recurrent_kernel_grouping_covers_every_utterance_once():
+    """Encoder._groups (CTA -> utterance grouping of e2e_lstm_sequence): consecutive, complete, at most 16 rows,
+    long utterances in small groups."""
+    from e2e_asr_pytorch_b200.model import Encoder
+    for lens in ([825, 700, 610, 599, 400, 301, 300, 299] + [180] * 37 + [3, 1], [5], [650] * 9):
+        first, rows = Encoder._groups(torch.tensor(lens))
+        assert first[0] == 0 and sum(rows) == len(lens)
+        assert all(f2 == f1 + r1 for f1, r1, f2 in zip(first, rows, first[1:]))
+        assert all(1 <= r <= 16 for r in rows)
+        for f, r in zip(first, rows):
+            assert r <= (4 if lens[f] >= 600 else (8 if lens[f] >= 300 else 16))
