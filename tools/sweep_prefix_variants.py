@@ -1,5 +1,16 @@
-"""Run the prefix-score micro-benchmark against tuning builds of the library (lib/variants/lib_<name>.so, built with
--DE2E_PS_MINBLOCKS / -DE2E_PS_UNROLL / -DE2E_PS_TILE) and print ms per launch for three launch shapes."""
+"""Run a micro-benchmark against tuning builds of the library (lib/variants/lib_<name>.so, built with
+-DE2E_PS_MINBLOCKS / -DE2E_PS_UNROLL / -DE2E_AF_MINBLOCKS ...) and print ms per launch for a few launch shapes.
+
+Build a variant next to the product library (git-ignored; it travels to the GPU box with the snapshot):
+
+    cd e2e-asr-pytorch_b200/csrc && mkdir -p ../lib/variants && nvcc -gencode arch=compute_100a,code=sm_100a -O3 \
+        -lineinfo -std=c++17 --expt-extended-lambda -Xcompiler -fPIC -shared -DE2E_PS_MINBLOCKS=4 \
+        -o ../lib/variants/lib_mb4.so *.cu
+
+    python tools/sweep_prefix_variants.py              # prefix-score micro-benchmark
+    python tools/sweep_prefix_variants.py attention    # attention micro-benchmark
+
+The library under test is selected with E2E_ASR_B200_LIB (e2e-asr-pytorch_b200/_lib.py)."""
 import glob, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 shapes = [["--utts", "2620"], ["--utts", "2620", "--plen", "60", "--skip-dead", "1"], ["--utts", "64", "--frames", "825"],
