@@ -23,6 +23,8 @@ then (3a) ``e2e_beam_candidates``, (2) ``e2e_ctc_prefix_score``, (3b)
 once per batch.  Nothing is copied to the host until the final N-best.
 There is no CPU fallback: inputs must live on a CUDA device.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -73,14 +75,17 @@ class _Fp32Math:
 
     def __enter__(self):
         mm = torch.backends.cuda.matmul
-        self.prev = (mm.allow_tf32, torch.backends.cudnn.allow_tf32, mm.allow_bf16_reduced_precision_reduction)
+        self.prev = (mm.allow_tf32, torch.backends.cudnn.allow_tf32, mm.allow_bf16_reduced_precision_reduction,
+                     mm.allow_fp16_reduced_precision_reduction)
         mm.allow_tf32 = False
         torch.backends.cudnn.allow_tf32 = False
         mm.allow_bf16_reduced_precision_reduction = False
+        mm.allow_fp16_reduced_precision_reduction = False
 
     def __exit__(self, *exc):
         mm = torch.backends.cuda.matmul
-        mm.allow_tf32, torch.backends.cudnn.allow_tf32, mm.allow_bf16_reduced_precision_reduction = self.prev
+        (mm.allow_tf32, torch.backends.cudnn.allow_tf32, mm.allow_bf16_reduced_precision_reduction,
+         mm.allow_fp16_reduced_precision_reduction) = self.prev
 
 
 class BeamDecoder(nn.Module):
@@ -120,6 +125,9 @@ class BeamDecoder(nn.Module):
         self.fast_math = False          # MUFU log-add-exp in the prefix-score kernel
         self.skip_dead_rows = True      # do not write state rows t < len(prefix) nobody reads back
         self.split_gemm = True          # fp32-accurate 3-way bf16 split of the recurrent GEMMs (stepper.py)
+        # operand format of the RNNLM's recurrent GEMMs: "bf16x3" (six partial products) or "fp16x2" (three; every
+        # input is a hidden state, |h| <= 1).  The environment variable is for A/B runs of the bench.
+        self.lm_split = os.environ.get("E2E_LM_SPLIT", "bf16x3")
         self.fused_attention = True     # hand-written location-aware attention kernel (csrc/attention_step.cu)
         self._stepper = None            # (device, split_gemm, stepper): weights are split once per device
         self.profile_prefix = False     # bench.py: CUDA-event pair around every prefix-score launch
@@ -188,10 +196,10 @@ class BeamDecoder(nn.Module):
 
         with _Fp32Math():
             mark("start")
-            knobs = (self.split_gemm, self.fused_attention)
+            knobs = (self.split_gemm, self.fused_attention, self.lm_split)
             if self._stepper is None or self._stepper[0] != dev or self._stepper[1] != knobs:
                 self._stepper = (dev, knobs, BatchedStepper(self.asr, self.lm if self.apply_lm else None,
-                                                            self.split_gemm, self.fused_attention))
+                                                            self.split_gemm, self.fused_attention, self.lm_split))
             stepper = self._stepper[2]
             stepper.mark = mark
             enc, enc_len = stepper.encode(audio_feature, feature_len.to(dev))

@@ -209,30 +209,52 @@ def attention_loc_full(key_t, value, query, prev_att, enc_len, w_conv, w_proj, w
     return attn, ctx
 
 
-def lstm_split_rows(src, row_idx, n, dst, k, off):
-    """dst[r, p*k + off : p*k + off + w] = p-th bf16 piece of src[row_idx[r]] (src [*,w] fp32, dst [>=n, 3k] bf16)."""
+def lstm_split_rows(src, row_idx, n, dst, k, off, scale=None):
+    """dst[r, p*k + off : p*k + off + w] = p-th piece of src[row_idx[r]] (src [*,w] fp32).  dst bf16 [>=n, 3k]: the exact
+    3-piece split; dst fp16 [>=n, 2k] (``scale`` = a power of two): the 2-piece split of scale*src."""
+    pieces = _pieces(dst, scale)
     _chk(src, F32, "src")
     _chk(row_idx, torch.int64, "row_idx", n)
-    _chk(dst, torch.bfloat16, "dst")
     w = src.shape[1]
-    if dst.shape[0] < n or dst.shape[1] < 3 * k:
+    if dst.shape[0] < n or dst.shape[1] < pieces * k:
         raise ValueError("lstm_split_rows: dst too small")
     if row_idx is None and src.shape[0] < n:
         raise ValueError("lstm_split_rows: src has fewer than n rows")
-    L.check(L.load().e2e_lstm_split_rows(L.ptr(src), int(src.stride(0)), L.ptr(row_idx), int(n), int(w),
-                                        L.ptr(dst), int(dst.stride(0)), int(k), int(off), _stream()))
+    if pieces == 3:
+        L.check(L.load().e2e_lstm_split_rows(L.ptr(src), int(src.stride(0)), L.ptr(row_idx), int(n), int(w),
+                                            L.ptr(dst), int(dst.stride(0)), int(k), int(off), _stream()))
+    else:
+        L.check(L.load().e2e_lstm_split_rows_f16x2(L.ptr(src), int(src.stride(0)), L.ptr(row_idx), int(n), int(w),
+                                                  L.ptr(dst), int(dst.stride(0)), int(k), int(off), float(scale), _stream()))
+
+
+def _pieces(dst, scale):
+    """Operand format of a split destination: 3 bf16 pieces, or 2 fp16 pieces of the scaled value."""
+    if dst is None:
+        return 3 if scale is None else 2
+    if not dst.is_cuda:
+        raise L.E2EError("split operand must be a CUDA tensor (no CPU path)")
+    if not dst.is_contiguous():
+        raise ValueError("split operand must be contiguous")
+    if dst.dtype == torch.bfloat16 and scale is None:
+        return 3
+    if dst.dtype == torch.float16 and scale is not None:
+        return 2
+    raise TypeError("split operand must be bf16 (3 pieces, no scale) or fp16 (2 pieces, with a scale), got %s" % dst.dtype)
 
 
 class SplitPlan:
     """Pre-marshalled argument arrays of e2e_lstm_split_rows_multi for a fixed set of (src, dst, K, off) pairs:
-    the per-step call then costs one ctypes dispatch."""
+    the per-step call then costs one ctypes dispatch.  ``scale`` selects the 2-piece fp16 format."""
 
-    def __init__(self, pairs):
+    def __init__(self, pairs, scale=None):
         import ctypes
         n = len(pairs)
         for src, dst, k, off in pairs:
             _chk(src, F32, "src")
-            _chk(dst, torch.bfloat16, "dst")
+            if _pieces(dst, scale) != (3 if scale is None else 2):
+                raise TypeError("SplitPlan: mixed operand formats")
+        self.scale = scale
         self.keep = pairs
         self.n = n
         self.srcs = (ctypes.c_void_p * n)(*[p[0].data_ptr() for p in pairs])
@@ -247,12 +269,19 @@ class SplitPlan:
     def run(self, row_idx, n_rows):
         if n_rows > self.rows or (row_idx is not None and (row_idx.dtype != torch.int64 or not row_idx.is_cuda or row_idx.numel() < n_rows)):
             raise ValueError("SplitPlan.run: bad row index / row count")
-        L.check(L.load().e2e_lstm_split_rows_multi(self.n, self.srcs, self.src_pitch, self.widths, self.dsts, self.dst_pitch,
-                                                  self.ks, self.offs, L.ptr(row_idx), int(n_rows), _stream()))
+        if self.scale is None:
+            L.check(L.load().e2e_lstm_split_rows_multi(self.n, self.srcs, self.src_pitch, self.widths, self.dsts, self.dst_pitch,
+                                                      self.ks, self.offs, L.ptr(row_idx), int(n_rows), _stream()))
+        else:
+            L.check(L.load().e2e_lstm_split_rows_multi_f16x2(self.n, self.srcs, self.src_pitch, self.widths, self.dsts, self.dst_pitch,
+                                                            self.ks, self.offs, L.ptr(row_idx), int(n_rows), float(self.scale), _stream()))
 
 
-def lstm_cell(gates, bias, c_prev, row_idx, n, c_new, h_new, table=None, tok=None, a_next=None, k_next=0, off_next=0):
-    """Fused LSTM cell (see e2e_lstm_cell): gates [>=n,4D] fp32 -> c_new, h_new [>=n,D] (+ split of h into a_next)."""
+def lstm_cell(gates, bias, c_prev, row_idx, n, c_new, h_new, table=None, tok=None, a_next=None, k_next=0, off_next=0,
+              gate_scale=None, next_scale=None):
+    """Fused LSTM cell (see e2e_lstm_cell): gates [>=n,4D] fp32 -> c_new, h_new [>=n,D] (+ split of h into a_next).
+    ``gate_scale`` (a power of two) selects the fp16x2 format: gates *= gate_scale first, a_next fp16 [>=n, 2*k_next]
+    receives the 2-piece split of next_scale*h."""
     _chk(gates, F32, "gates")
     _chk(bias, F32, "bias")
     _chk(c_prev, F32, "c_prev")
@@ -261,13 +290,22 @@ def lstm_cell(gates, bias, c_prev, row_idx, n, c_new, h_new, table=None, tok=Non
     _chk(h_new, F32, "h_new")
     _chk(table, F32, "table")
     _chk(tok, torch.int64, "tok", n)
-    _chk(a_next, torch.bfloat16, "a_next")
+    f16 = gate_scale is not None
+    if a_next is not None and _pieces(a_next, next_scale if f16 else None) != (2 if f16 else 3):
+        raise TypeError("lstm_cell: a_next does not match the operand format")
     d = c_prev.shape[1]
     if gates.shape[0] < n or gates.shape[1] < 4 * d or c_new.shape[0] < n or h_new.shape[0] < n or bias.numel() < 4 * d:
         raise ValueError("lstm_cell: inconsistent shapes")
-    L.check(L.load().e2e_lstm_cell(L.ptr(gates), int(gates.stride(0)), L.ptr(bias), L.ptr(table), L.ptr(tok), L.ptr(c_prev),
-                                  L.ptr(row_idx), int(n), int(d), L.ptr(c_new), L.ptr(h_new), L.ptr(a_next),
-                                  int(a_next.stride(0)) if a_next is not None else 0, int(k_next), int(off_next), _stream()))
+    a_pitch = int(a_next.stride(0)) if a_next is not None else 0
+    if not f16:
+        L.check(L.load().e2e_lstm_cell(L.ptr(gates), int(gates.stride(0)), L.ptr(bias), L.ptr(table), L.ptr(tok), L.ptr(c_prev),
+                                      L.ptr(row_idx), int(n), int(d), L.ptr(c_new), L.ptr(h_new), L.ptr(a_next),
+                                      a_pitch, int(k_next), int(off_next), _stream()))
+    else:
+        L.check(L.load().e2e_lstm_cell_f16x2(L.ptr(gates), int(gates.stride(0)), float(gate_scale), L.ptr(bias), L.ptr(table), L.ptr(tok),
+                                            L.ptr(c_prev), L.ptr(row_idx), int(n), int(d), L.ptr(c_new), L.ptr(h_new), L.ptr(a_next),
+                                            a_pitch, int(k_next), int(off_next), float(next_scale if next_scale is not None else 1.0),
+                                            _stream()))
 
 
 def conv3x3_unfold_split(x_nhwc, valid_rows, first_pixel, n_pixels, out):

@@ -77,6 +77,44 @@ class SplitLinear:
         return y if self.bias is None else y + self.bias
 
 
+F16_ACT_SCALE = 2.0 ** 14     # |h| <= 1 for an LSTM hidden state: scale*h stays far inside fp16's range (65504)
+
+
+def _split2_f16(x, scale):
+    """fp32 -> two fp16 tensors with scale*x == a1 + a2 up to 2^-22 |scale*x| (scale a power of two)."""
+    xs = x * scale
+    a1 = xs.to(torch.float16)
+    a2 = (xs - a1.float()).to(torch.float16)
+    return a1, a2
+
+
+class SplitLinearF16:
+    """y = x @ W^T on fp16 tensor cores from 2-piece splits: s_a*x = a1+a2, s_w*W = w1+w2 (22 mantissa bits each),
+    three partial products grouped by magnitude — {a1w1}, {a1w2, a2w1} — smallest group first through the fp32 C
+    operand, HALF the tensor-core work of SplitLinear's six.  Only for operands of known range (LSTM hidden states):
+    fp16 has 5 exponent bits, so the scales must keep every piece that matters out of the subnormals and the largest
+    below 65504.  s_w puts the largest |W| in [2^13, 2^14).  The product carries the factor s_a*s_w (``1/out_scale``),
+    a power of two the cell kernel removes exactly.  Representation error of the operands: 2^-22 relative (bf16x3:
+    2^-24), below the fp32 accumulation error of a K >= 1024 dot product (tests/test_host_logic.py checks the budget
+    against float64)."""
+
+    def __init__(self, weight, act_scale=F16_ACT_SCALE):
+        w = weight.detach().float()
+        w_max = float(w.abs().max())
+        self.w_scale = 2.0 ** (13 - int(np.floor(np.log2(w_max)))) if w_max > 0 else 1.0
+        w1, w2 = _split2_f16(w, self.w_scale)
+        self.b0 = w1.t().contiguous()                                   # [K, M]
+        self.b1 = torch.cat([w2, w1], dim=1).t().contiguous()           # [2K, M]:  [a1 | a2] @ [w2; w1]
+        self.act_scale = float(act_scale)
+        self.out_scale = 1.0 / (self.act_scale * self.w_scale)
+
+    def __call__(self, x):
+        a1, a2 = _split2_f16(x, self.act_scale)
+        y = torch.mm(torch.cat([a1, a2], dim=1), self.b1, out_dtype=torch.float32)
+        y = torch.addmm(y, a1, self.b0, out_dtype=torch.float32)
+        return y * self.out_scale
+
+
 class _Rnn:
     """n-layer LSTM/GRU advanced one token at a time for a batch of rows.  States are lists of
     per-layer [N, D] tensors so that row prefixes are contiguous views."""
@@ -144,9 +182,19 @@ class _FusedLstm:
     (SURVEY §8f row f-2): per layer one hand-written split kernel, the three split GEMMs (library,
     tensor cores, fp32 accumulation) and one hand-written cell kernel (csrc/lstm_step.cu).  States
     are never permuted: a step reads the previous states through the parents' row index ``idx``
-    and writes the new ones to the other half of a ping-pong buffer."""
+    and writes the new ones to the other half of a ping-pong buffer.
 
-    def __init__(self, rnn, first_input_table=None):
+    ``split`` selects the GEMM operand format: "bf16x3" (exact 3-piece bf16 split, six partial products, any operand
+    range) or "fp16x2" (2-piece fp16 split, three partial products; needs a tabled layer 0 so that every GEMM input
+    is a hidden state, |h| <= 1 — the RNNLM, src/lm.py:27-38)."""
+
+    def __init__(self, rnn, first_input_table=None, split="bf16x3"):
+        if split not in ("bf16x3", "fp16x2"):
+            raise ValueError("unknown split format " + str(split))
+        if split == "fp16x2" and first_input_table is None:
+            raise NotImplementedError("the fp16x2 operand format needs a tabled layer 0 (inputs of unknown range)")
+        self.f16 = split == "fp16x2"
+        make_lin = SplitLinearF16 if self.f16 else SplitLinear
         self.layers, self.dim = rnn.num_layers, rnn.hidden_size
         self.lin, self.bias, self.k_in, self.table0 = [], [], [], None
         for l in range(self.layers):
@@ -155,11 +203,11 @@ class _FusedLstm:
             if l == 0 and first_input_table is not None:
                 # layer 0 sees one of V embeddings: its input projection is a [V, 4D] table
                 self.table0 = (first_input_table.double() @ w_ih.double().t() + b_ih.double()).float().contiguous()
-                self.lin.append(SplitLinear(w_hh))
+                self.lin.append(make_lin(w_hh))
                 self.bias.append(b_hh.contiguous())
                 self.k_in.append(0)
             else:
-                self.lin.append(SplitLinear(torch.cat([w_ih, w_hh], dim=1)))
+                self.lin.append(make_lin(torch.cat([w_ih, w_hh], dim=1)))
                 self.bias.append((b_ih + b_hh).contiguous())
                 self.k_in.append(w_ih.shape[1])
         self.cur = 0
@@ -168,13 +216,15 @@ class _FusedLstm:
         d = self.dim
         self.h = [[torch.zeros(n, d, device=device) for _ in range(self.layers)] for _ in range(2)]
         self.c = [[torch.zeros(n, d, device=device) for _ in range(self.layers)] for _ in range(2)]
-        self.a = [torch.empty(n, 3 * (self.k_in[l] + d), dtype=torch.bfloat16, device=device) for l in range(self.layers)]
+        pieces, a_dtype = (2, torch.float16) if self.f16 else (3, torch.bfloat16)
+        self.a = [torch.empty(n, pieces * (self.k_in[l] + d), dtype=a_dtype, device=device) for l in range(self.layers)]
         self.gates = torch.empty(n, 4 * d, device=device)          # GEMM accumulator, reused by every layer
         self.idx = torch.arange(n, device=device)
         self.cur = 0
         from . import ops
         vec = d % 4 == 0 and all(k % 4 == 0 for k in self.k_in)
-        self.plans = [ops.SplitPlan([(self.h[c][l], self.a[l], self.k_in[l] + d, self.k_in[l]) for l in range(self.layers)])
+        self.scale = F16_ACT_SCALE if self.f16 else None
+        self.plans = [ops.SplitPlan([(self.h[c][l], self.a[l], self.k_in[l] + d, self.k_in[l]) for l in range(self.layers)], self.scale)
                       if (vec and self.layers <= 8) else None for c in range(2)]
 
     def hidden(self, n):
@@ -191,20 +241,24 @@ class _FusedLstm:
             self.plans[cur].run(idx, n)
         else:
             for l in range(self.layers):
-                ops.lstm_split_rows(self.h[cur][l], idx, n, self.a[l], self.k_in[l] + d, self.k_in[l])
+                ops.lstm_split_rows(self.h[cur][l], idx, n, self.a[l], self.k_in[l] + d, self.k_in[l], self.scale)
         if self.k_in[0] > 0:
             ops.lstm_split_rows(x0.contiguous(), None, n, self.a[0], self.k_in[0] + d, 0)
         for l in range(self.layers):
             k = self.k_in[l] + d
             a, lin = self.a[l][:n], self.lin[l]
             y = self.gates[:n]                                         # accumulate in place: no C-operand copies
-            torch.mm(a, lin.b2, out_dtype=torch.float32, out=y)
-            torch.addmm(y, a[:, :2 * k], lin.b1, out_dtype=torch.float32, out=y)
+            if self.f16:
+                torch.mm(a, lin.b1, out_dtype=torch.float32, out=y)
+            else:
+                torch.mm(a, lin.b2, out_dtype=torch.float32, out=y)
+                torch.addmm(y, a[:, :2 * k], lin.b1, out_dtype=torch.float32, out=y)
             torch.addmm(y, a[:, :k], lin.b0, out_dtype=torch.float32, out=y)
             nxt = l + 1 < self.layers
             ops.lstm_cell(y, self.bias[l], self.c[cur][l], idx, n, self.c[new][l], self.h[new][l],
                           table=self.table0 if l == 0 else None, tok=tok if (l == 0 and self.table0 is not None) else None,
-                          a_next=self.a[l + 1] if nxt else None, k_next=(self.k_in[l + 1] + d) if nxt else 0, off_next=0)
+                          a_next=self.a[l + 1] if nxt else None, k_next=(self.k_in[l + 1] + d) if nxt else 0, off_next=0,
+                          gate_scale=lin.out_scale if self.f16 else None, next_scale=self.scale)
         self.cur = new
         return self.h[new][self.layers - 1][:n]
 
@@ -213,7 +267,7 @@ class _FusedLstm:
 
 
 class BatchedStepper:
-    def __init__(self, asr, lm=None, split_gemm=False, fused_attention=False):
+    def __init__(self, asr, lm=None, split_gemm=False, fused_attention=False, lm_split="bf16x3"):
         att = asr.attention
         if att.num_head != 1:
             raise NotImplementedError("multi-head attention is not supported by the batched beam search")
@@ -224,13 +278,13 @@ class BatchedStepper:
         self.mode, self.temperature = att.mode, att.att_layer.temperature
         # fused device LSTM steps (csrc/lstm_step.cu) whenever the weights live on a GPU; the plain
         # PyTorch cells otherwise (CPU tests of the host logic, GRU models)
-        def make(rnn, table=None):
+        def make(rnn, table=None, split="bf16x3"):
             on_gpu = next(rnn.parameters()).is_cuda
             if split_gemm and on_gpu and isinstance(rnn, torch.nn.LSTM):
-                return _FusedLstm(rnn, table)
+                return _FusedLstm(rnn, table, split)
             return _Rnn(rnn, split_gemm, table)
-        self.dec = make(asr.decoder.layers)
-        self.lm_rnn = make(lm.rnn, lm.emb.weight.detach()) if lm is not None else None
+        self.dec = make(asr.decoder.layers)                  # speller inputs (embedding, context) have no fixed range: bf16x3
+        self.lm_rnn = make(lm.rnn, lm.emb.weight.detach(), lm_split) if lm is not None else None
         self.mark = lambda name: None            # profiling hook (decode.py sets it)
         self.fused_attention = False
         if fused_attention and self.mode == "loc":

@@ -227,6 +227,24 @@ int e2e_lstm_cell(const float *gates, long long gates_pitch, const float *bias, 
                   float *c_new, float *h_new, void *a_next_bf16, long long a_pitch, int K_next, int off_next,
                   void *stream);
 
+/* The same three entry points for the 2-piece fp16 operand format (src/lm.py:27-38 only: every GEMM input of the RNNLM
+ * step is an LSTM hidden state, |h| < 1, so a fixed power-of-two scale keeps both pieces in fp16's normal range):
+ *   piece_0 = fp16(scale*x), piece_1 = fp16(scale*x - piece_0), scale*x == piece_0 + piece_1 up to 2^-22 |scale*x|;
+ *   dst fp16 [n][dst_pitch >= 2*K]: the A operand [a1 | a2].  Against weights split the same way
+ *   (scale_w*W == w1 + w2) three partial products a1 w1 + (a1 w2 + a2 w1) replace the six of the bf16 format — half the
+ *   tensor-core work — and the GEMM result is (scale*scale_w) * (x W^T):
+ * e2e_lstm_cell_f16x2 multiplies the gates by gate_scale = 1/(scale*scale_w) (exact, a power of two) before the bias
+ * is added, and writes h' as the 2-piece split of next_scale*h'.  All scales must be powers of two in 2^-60..2^60. */
+int e2e_lstm_split_rows_f16x2(const float *src, long long src_pitch, const long long *row_idx, int n, int w,
+                              void *dst_f16, long long dst_pitch, int K, int off, float scale, void *stream);
+int e2e_lstm_split_rows_multi_f16x2(int n_src, const float *const *srcs_host, const long long *src_pitches_host, const int *widths_host,
+                                    void *const *dsts_f16_host, const long long *dst_pitches_host, const int *Ks_host, const int *offs_host,
+                                    const long long *row_idx, int n, float scale, void *stream);
+int e2e_lstm_cell_f16x2(const float *gates, long long gates_pitch, float gate_scale, const float *bias, const float *table,
+                        const long long *tok, const float *c_prev, const long long *row_idx, int n, int D,
+                        float *c_new, float *h_new, void *a_next_f16, long long a_pitch, int K_next, int off_next,
+                        float next_scale, void *stream);
+
 /* (next) 3x3 "same" convolutions of the VGG front end (src/module.py:672-686) as
  * fp32-accurate tensor-core GEMMs: unfold a block of NHWC pixels into the GEMM's A operand as the exact
  * 3-piece bf16 split [a1 | a2 | a3] of every fp32 value,

@@ -159,3 +159,30 @@ def test_recurrent_kernel_grouping_covers_every_utterance_once():
         assert all(1 <= r <= 16 for r in rows)
         for f, r in zip(first, rows):
             assert r <= (4 if lens[f] >= 600 else (8 if lens[f] >= 300 else 16))
+
+
+def test_f16x2_split_error_budget_against_float64():
+    """stepper.SplitLinearF16 (the opt-in 2-piece fp16 operand format of the RNNLM GEMMs), restated with fp32 matmuls of
+    its own pieces: the operands' representation error (2^-22) stays below the fp32 accumulation error of the
+    product itself, the weight scale puts the largest weight in [2^13, 2^14), and nothing overflows fp16."""
+    import torch
+    from e2e_asr_pytorch_b200.stepper import SplitLinearF16, _split2_f16, F16_ACT_SCALE
+    g = torch.Generator().manual_seed(0)
+    x = torch.tanh(torch.randn(192, 2048, generator=g) * 2)
+    x[0, :3] = torch.tensor([1.0, -1.0, 1e-7])
+    w = (torch.rand(1024, 2048, generator=g) * 2 - 1) / 32
+    lin = SplitLinearF16(w)
+    assert 2.0 ** 13 <= float(w.abs().max()) * lin.w_scale < 2.0 ** 14
+    assert lin.b0.dtype == torch.float16 and torch.isfinite(lin.b1.float()).all()
+    a1, a2 = _split2_f16(x, F16_ACT_SCALE)
+    assert torch.isfinite(a1.float()).all() and float(a1.float().abs().max()) <= 2.0 ** 14
+    back = (a1.double() + a2.double()) / F16_ACT_SCALE
+    assert float((back - x.double()).abs().max()) <= 2.0 ** -22
+    want = x.double() @ w.double().t()
+    y = (torch.cat([a1, a2], dim=1).float() @ lin.b1.float() + a1.float() @ lin.b0.float()) * lin.out_scale
+    exact_acc = (torch.cat([a1, a2], dim=1).double() @ lin.b1.double() + a1.double() @ lin.b0.double()) * lin.out_scale
+    e_repr = float((exact_acc - want).abs().max())
+    e_split = float((y.double() - want).abs().max())
+    e_fp32 = float(((x @ w.t()).double() - want).abs().max())
+    assert e_repr < 0.5 * e_fp32, (e_repr, e_fp32)
+    assert e_split <= 2.0 * e_fp32 + 1e-7, (e_split, e_fp32)
