@@ -4,10 +4,15 @@ test_gpu_kernels.py / test_gpu_decode.py: pieces bit-equal to their torch restat
 float64, GEMM as accurate as the library's fp32 GEMM, LSTM stack within 2e-6 of nn.LSTM in float64, and the
 decode's 1-best identical to the oracle's.  The format is opt-in (BeamDecoder.lm_split = "fp16x2").
 """
+import os
+
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+# Written without a GPU at hand: until a run on the B200 has confirmed them they only run on request, so that the
+# suite the driver runs stays exactly the one that was last seen green.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("E2E_UNVALIDATED_TESTS") != "1", reason="not yet confirmed on a B200 (set E2E_UNVALIDATED_TESTS=1)")]
 
 SCALE = 2.0 ** 14
 
