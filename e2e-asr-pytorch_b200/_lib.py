@@ -73,6 +73,14 @@ SIGNATURES = {
     "e2e_conv1_direct": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p]),
     "e2e_conv_bias_relu_mask_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "e2e_conv1_direct_amax": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_void_p, c_void_p]),
+    "e2e_conv3x3_unfold_split_f16x2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.c_longlong, c_int, c_void_p,
+                                               c_void_p, c_void_p]),
+    "e2e_conv_bias_relu_mask_scaled": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.c_longlong,
+                                               ctypes.c_longlong, c_void_p, c_float, c_void_p, c_void_p]),
+    "e2e_conv_bias_relu_mask_pool_scaled": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
+                                                    c_void_p, c_void_p]),
     "e2e_beam_finalize": (c_int, [c_int, c_int, c_void_p,
                                   c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p,

@@ -128,6 +128,9 @@ class BeamDecoder(nn.Module):
         # operand format of the RNNLM's recurrent GEMMs: "bf16x3" (six partial products) or "fp16x2" (three; every
         # input is a hidden state, |h| <= 1).  The environment variable is for A/B runs of the bench.
         self.lm_split = os.environ.get("E2E_LM_SPLIT", "bf16x3")
+        # the same choice for the VGG convolutions (their activations have no fixed range: the scale is chosen on
+        # the device from the running maximum of every layer's input, csrc/conv_split.cu)
+        self.vgg_split = os.environ.get("E2E_VGG_SPLIT", "bf16x3")
         self.fused_attention = True     # hand-written location-aware attention kernel (csrc/attention_step.cu)
         self._stepper = None            # (device, split_gemm, stepper): weights are split once per device
         self.profile_prefix = False     # bench.py: CUDA-event pair around every prefix-score launch
@@ -196,10 +199,10 @@ class BeamDecoder(nn.Module):
 
         with _Fp32Math():
             mark("start")
-            knobs = (self.split_gemm, self.fused_attention, self.lm_split)
+            knobs = (self.split_gemm, self.fused_attention, self.lm_split, self.vgg_split)
             if self._stepper is None or self._stepper[0] != dev or self._stepper[1] != knobs:
                 self._stepper = (dev, knobs, BatchedStepper(self.asr, self.lm if self.apply_lm else None,
-                                                            self.split_gemm, self.fused_attention, self.lm_split))
+                                                            self.split_gemm, self.fused_attention, self.lm_split, self.vgg_split))
             stepper = self._stepper[2]
             stepper.mark = mark
             enc, enc_len = stepper.encode(audio_feature, feature_len.to(dev))

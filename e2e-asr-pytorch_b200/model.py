@@ -138,40 +138,50 @@ class VGGFrontEnd(nn.Module):
     # -- fp32-accurate tensor-core path (CUDA only; SURVEY §8f row f-4) ---------------------------------
     A_BYTES = 3 << 30      # budget of the unfolded bf16 operand per GEMM block
 
+    conv_split_format = "bf16x3"     # "fp16x2": 2-piece fp16 operands, scale per layer input chosen on the device (csrc/conv_split.cu)
+
     def _split_weights(self, conv):
-        """[9*Cin, Cout] GEMM weights of a 3x3 convolution as the three bf16 operand stacks of
-        stepper.SplitLinear (k = (dy*3+dx)*Cin + c), cached per layer and device."""
-        from .stepper import SplitLinear
+        """[9*Cin, Cout] GEMM weights of a 3x3 convolution as the operand stacks of stepper.SplitLinear /
+        SplitLinearF16 (k = (dy*3+dx)*Cin + c), cached per layer, device and format."""
+        from .stepper import SplitLinear, SplitLinearF16
         cache = self.__dict__.setdefault("_split_cache", {})
-        key = (id(conv), conv.weight.device)
+        key = (id(conv), conv.weight.device, self.conv_split_format)
         if key not in cache:
             w2d = conv.weight.detach().permute(2, 3, 1, 0).reshape(-1, conv.out_channels).t().contiguous()   # [Cout, 9*Cin]
-            cache[key] = SplitLinear(w2d)
+            cache[key] = SplitLinearF16(w2d, act_scale=1.0) if self.conv_split_format == "fp16x2" else SplitLinear(w2d)
         return cache[key]
 
-    def _conv_split(self, x, valid, conv, pool=False):
+    def _conv_split(self, x, valid, conv, pool=False, amax_in=None, amax_out=None):
         """x [N,H,W,C] fp32 NHWC, valid [N] int32 -> relu(conv(x) + b) [N,H,W,Cout] NHWC, rows >= valid zeroed;
-        with ``pool`` the 2x2 ceil-mode max pooling that follows is fused into the epilogue kernel."""
+        with ``pool`` the 2x2 ceil-mode max pooling that follows is fused into the epilogue kernel.
+        ``amax_in`` / ``amax_out`` (int32 [1] device words) select the fp16x2 format: the scale of this layer's
+        operand comes from amax_in, the maximum of its output goes to amax_out."""
         from . import ops
         n, h, w, c = x.shape
         k = 9 * c
         lin = self._split_weights(conv)
         total = n * h * w
-        blk = max(1, min(total, self.A_BYTES // (3 * k * 2)))
-        a = torch.empty((blk, 3 * k), dtype=torch.bfloat16, device=x.device)
+        f16 = amax_in is not None
+        pieces, a_dtype = (2, torch.float16) if f16 else (3, torch.bfloat16)
+        blk = max(1, min(total, self.A_BYTES // (pieces * k * 2)))
+        a = torch.empty((blk, pieces * k), dtype=a_dtype, device=x.device)
         y = torch.empty((total, conv.out_channels), dtype=torch.float32, device=x.device)
         for p0 in range(0, total, blk):
             m = min(blk, total - p0)
-            ops.conv3x3_unfold_split(x, valid, p0, m, a)
+            ops.conv3x3_unfold_split(x, valid, p0, m, a, amax=amax_in)
             am, ym = a[:m], y[p0:p0 + m]
-            torch.mm(am, lin.b2, out_dtype=torch.float32, out=ym)                      # a1w3 + a2w2 + a3w1
-            torch.addmm(ym, am[:, :2 * k], lin.b1, out_dtype=torch.float32, out=ym)    # + a1w2 + a2w1
-            torch.addmm(ym, am[:, :k], lin.b0, out_dtype=torch.float32, out=ym)        # + a1w1
+            if f16:
+                torch.mm(am, lin.b1, out_dtype=torch.float32, out=ym)                      # a1w2 + a2w1
+            else:
+                torch.mm(am, lin.b2, out_dtype=torch.float32, out=ym)                      # a1w3 + a2w2 + a3w1
+                torch.addmm(ym, am[:, :2 * k], lin.b1, out_dtype=torch.float32, out=ym)    # + a1w2 + a2w1
+            torch.addmm(ym, am[:, :k], lin.b0, out_dtype=torch.float32, out=ym)            # + a1w1
         y = y.view(n, h, w, conv.out_channels)
         bias = conv.bias.detach().float().contiguous()
+        scale_args = (amax_in, lin.out_scale, amax_out) if f16 else ()
         if pool:
-            return ops.conv_bias_relu_mask_pool(y, bias, valid)
-        ops.conv_bias_relu_mask(y, bias, valid)
+            return ops.conv_bias_relu_mask_pool(y, bias, valid, *scale_args)
+        ops.conv_bias_relu_mask(y, bias, valid, *scale_args)
         return y
 
     def forward_masked_split(self, feat, feat_len):
@@ -190,10 +200,14 @@ class VGGFrontEnd(nn.Module):
         v2 = (own // 2).to(torch.int32).contiguous()
         convs = [m for m in self.extractor if isinstance(m, nn.Conv2d)]
         w1 = convs[0].weight.detach().float().contiguous()
-        y = ops.conv1_direct(feat, w1, convs[0].bias.detach().float().contiguous(), v1, self.freq_dim)   # [N,L,F,C1]
-        y = self._conv_split(y, v1, convs[1], pool=True)                               # rows >= own read as zero inside
-        y = self._conv_split(y, v2, convs[2])
-        y = self._conv_split(y, v2, convs[3], pool=True)                               # [N, T/4, F/4, C2]
+        f16 = self.conv_split_format == "fp16x2"
+        # scale words (float bits of max|x|) of the inputs of conv2, conv3, conv4 and of the output, written on the device
+        amax = torch.zeros(4, dtype=torch.int32, device=feat.device) if f16 else None
+        word = lambda i: amax[i:i + 1] if f16 else None
+        y = ops.conv1_direct(feat, w1, convs[0].bias.detach().float().contiguous(), v1, self.freq_dim, amax_out=word(0))   # [N,L,F,C1]
+        y = self._conv_split(y, v1, convs[1], pool=True, amax_in=word(0), amax_out=word(1))   # rows >= own read as zero inside
+        y = self._conv_split(y, v2, convs[2], amax_in=word(1), amax_out=word(2))
+        y = self._conv_split(y, v2, convs[3], pool=True, amax_in=word(2), amax_out=word(3))   # [N, T/4, F/4, C2]
         out = y.permute(0, 1, 3, 2).contiguous()                                       # [N, T/4, C2, F/4]
         return out.view(out.shape[0], out.shape[1], self.out_dim), feat_len // 4
 

@@ -308,23 +308,38 @@ def lstm_cell(gates, bias, c_prev, row_idx, n, c_new, h_new, table=None, tok=Non
                                             _stream()))
 
 
-def conv3x3_unfold_split(x_nhwc, valid_rows, first_pixel, n_pixels, out):
-    """Unfold + 3-piece bf16 split of a block of NHWC pixels (see e2e_conv3x3_unfold_split): out [>=n_pixels, 27*C]."""
+def conv3x3_unfold_split(x_nhwc, valid_rows, first_pixel, n_pixels, out, amax=None):
+    """Unfold + split of a block of NHWC pixels (see e2e_conv3x3_unfold_split): out bf16 [>=n_pixels, 27*C] (exact 3-piece
+    split), or fp16 [>=n_pixels, 18*C] with ``amax`` (int32 [1]: float bits of the input's maximum) for the 2-piece format."""
     _chk(x_nhwc, F32, "x_nhwc")
     _chk(valid_rows, I32, "valid_rows", x_nhwc.shape[0])
-    _chk(out, torch.bfloat16, "out", n_pixels * 27 * x_nhwc.shape[3])
     n, h, w, c = x_nhwc.shape
-    L.check(L.load().e2e_conv3x3_unfold_split(L.ptr(x_nhwc), L.ptr(valid_rows), n, h, w, c, int(first_pixel), int(n_pixels),
-                                             L.ptr(out), _stream()))
+    if amax is None:
+        _chk(out, torch.bfloat16, "out", n_pixels * 27 * c)
+        L.check(L.load().e2e_conv3x3_unfold_split(L.ptr(x_nhwc), L.ptr(valid_rows), n, h, w, c, int(first_pixel), int(n_pixels),
+                                                 L.ptr(out), _stream()))
+    else:
+        _chk(out, torch.float16, "out", n_pixels * 18 * c)
+        _chk(amax, I32, "amax", 1)
+        L.check(L.load().e2e_conv3x3_unfold_split_f16x2(L.ptr(x_nhwc), L.ptr(valid_rows), n, h, w, c, int(first_pixel), int(n_pixels),
+                                                       L.ptr(amax), L.ptr(out), _stream()))
 
 
-def conv_bias_relu_mask(y_nhwc, bias, valid_rows):
-    """In place: y = relu(y + bias) on rows h < valid_rows[n], 0 elsewhere; y [N,H,W,C] NHWC."""
+def conv_bias_relu_mask(y_nhwc, bias, valid_rows, amax_in=None, inv_w_scale=None, amax_out=None):
+    """In place: y = relu(y + bias) on rows h < valid_rows[n], 0 elsewhere; y [N,H,W,C] NHWC.  With ``amax_in`` (the scale
+    word of the layer's INPUT) y is an fp16x2 GEMM result: it is first multiplied by inv_w_scale / act_scale(amax_in);
+    the maximum of the result goes to ``amax_out`` (the next layer's scale word)."""
     _chk(y_nhwc, F32, "y_nhwc")
     _chk(bias, F32, "bias", y_nhwc.shape[3])
     _chk(valid_rows, I32, "valid_rows", y_nhwc.shape[0])
     n, h, w, c = y_nhwc.shape
-    L.check(L.load().e2e_conv_bias_relu_mask(L.ptr(y_nhwc), L.ptr(bias), L.ptr(valid_rows), n, h, w, c, 0, n * h * w, _stream()))
+    if amax_in is None:
+        L.check(L.load().e2e_conv_bias_relu_mask(L.ptr(y_nhwc), L.ptr(bias), L.ptr(valid_rows), n, h, w, c, 0, n * h * w, _stream()))
+    else:
+        _chk(amax_in, I32, "amax_in", 1)
+        _chk(amax_out, I32, "amax_out", 1)
+        L.check(L.load().e2e_conv_bias_relu_mask_scaled(L.ptr(y_nhwc), L.ptr(bias), L.ptr(valid_rows), n, h, w, c, 0, n * h * w,
+                                                       L.ptr(amax_in), float(inv_w_scale), L.ptr(amax_out), _stream()))
 
 
 def lstm_sequence(gates, out, frame_off, lens, group_first, group_rows, hidden, fw, bw=None):
@@ -347,12 +362,14 @@ def lstm_sequence(gates, out, frame_off, lens, group_first, group_rows, hidden, 
                                       L.ptr(bw[0]), L.ptr(bw[1]), int(bw[2]), int(bw[3]), _stream()))
 
 
-def conv1_direct(feat, weight, bias, valid_rows, n_freq):
+def conv1_direct(feat, weight, bias, valid_rows, n_freq, amax_out=None):
     """First VGG layer from the feature frames: feat [N,L,Cin*F] (last dim contiguous, rows of an utterance contiguous)
-    -> relu(conv + bias) [N,L,F,Cout] NHWC."""
+    -> relu(conv + bias) [N,L,F,Cout] NHWC.  ``amax_out`` (int32 [1], zeroed by the caller) receives the float bits of the
+    maximum over the valid rows (the scale word of the next layer's fp16x2 operand)."""
     _chk(weight, F32, "weight")
     _chk(bias, F32, "bias")
     _chk(valid_rows, I32, "valid_rows", feat.shape[0])
+    _chk(amax_out, I32, "amax_out", 1)
     if not feat.is_cuda or feat.dtype != F32 or feat.stride(2) != 1 or feat.stride(1) != feat.shape[2]:
         raise ValueError("conv1_direct: feat must be a CUDA fp32 [N,L,D] tensor with contiguous utterances")
     n, l, d = feat.shape
@@ -360,19 +377,30 @@ def conv1_direct(feat, weight, bias, valid_rows, n_freq):
     if d != cin * n_freq:
         raise ValueError("conv1_direct: feature width %d != Cin*F" % d)
     out = torch.empty((n, l, n_freq, cout), dtype=F32, device=feat.device)
-    L.check(L.load().e2e_conv1_direct(L.ptr(feat), int(feat.stride(0)), L.ptr(weight), L.ptr(bias), L.ptr(valid_rows),
-                                     n, l, int(n_freq), int(cin), int(cout), L.ptr(out), _stream()))
+    if amax_out is None:
+        L.check(L.load().e2e_conv1_direct(L.ptr(feat), int(feat.stride(0)), L.ptr(weight), L.ptr(bias), L.ptr(valid_rows),
+                                         n, l, int(n_freq), int(cin), int(cout), L.ptr(out), _stream()))
+    else:
+        L.check(L.load().e2e_conv1_direct_amax(L.ptr(feat), int(feat.stride(0)), L.ptr(weight), L.ptr(bias), L.ptr(valid_rows),
+                                              n, l, int(n_freq), int(cin), int(cout), L.ptr(out), L.ptr(amax_out), _stream()))
     return out
 
 
-def conv_bias_relu_mask_pool(y_nhwc, bias, valid_rows):
-    """max_pool2d(2, 2, ceil_mode=True) of mask(relu(y + bias)); y [N,H,W,C] NHWC -> [N,ceil(H/2),ceil(W/2),C]."""
+def conv_bias_relu_mask_pool(y_nhwc, bias, valid_rows, amax_in=None, inv_w_scale=None, amax_out=None):
+    """max_pool2d(2, 2, ceil_mode=True) of mask(relu(y + bias)); y [N,H,W,C] NHWC -> [N,ceil(H/2),ceil(W/2),C].
+    ``amax_in`` / ``inv_w_scale`` / ``amax_out`` as in conv_bias_relu_mask."""
     _chk(y_nhwc, F32, "y_nhwc")
     _chk(bias, F32, "bias", y_nhwc.shape[3])
     _chk(valid_rows, I32, "valid_rows", y_nhwc.shape[0])
     n, h, w, c = y_nhwc.shape
     out = torch.empty((n, (h + 1) // 2, (w + 1) // 2, c), dtype=F32, device=y_nhwc.device)
-    L.check(L.load().e2e_conv_bias_relu_mask_pool(L.ptr(y_nhwc), L.ptr(bias), L.ptr(valid_rows), n, h, w, c, L.ptr(out), _stream()))
+    if amax_in is None:
+        L.check(L.load().e2e_conv_bias_relu_mask_pool(L.ptr(y_nhwc), L.ptr(bias), L.ptr(valid_rows), n, h, w, c, L.ptr(out), _stream()))
+    else:
+        _chk(amax_in, I32, "amax_in", 1)
+        _chk(amax_out, I32, "amax_out", 1)
+        L.check(L.load().e2e_conv_bias_relu_mask_pool_scaled(L.ptr(y_nhwc), L.ptr(bias), L.ptr(valid_rows), n, h, w, c, L.ptr(out),
+                                                            L.ptr(amax_in), float(inv_w_scale), L.ptr(amax_out), _stream()))
     return out
 
 

@@ -267,14 +267,17 @@ class _FusedLstm:
 
 
 class BatchedStepper:
-    def __init__(self, asr, lm=None, split_gemm=False, fused_attention=False, lm_split="bf16x3"):
+    def __init__(self, asr, lm=None, split_gemm=False, fused_attention=False, lm_split="bf16x3", vgg_split="bf16x3"):
         att = asr.attention
         if att.num_head != 1:
             raise NotImplementedError("multi-head attention is not supported by the batched beam search")
         if att.mode not in ("loc", "dot"):
             raise NotImplementedError("attention mode " + str(att.mode))
         self.asr, self.lm = asr, lm
-        self.split_conv = bool(split_gemm)       # VGG convolutions as fp32-accurate bf16 tensor-core GEMMs (model.py)
+        self.split_conv = bool(split_gemm)       # VGG convolutions as fp32-accurate tensor-core GEMMs (model.py)
+        if vgg_split not in ("bf16x3", "fp16x2"):
+            raise ValueError("unknown split format " + str(vgg_split))
+        self.vgg_split = vgg_split               # their operand format
         self.mode, self.temperature = att.mode, att.att_layer.temperature
         # fused device LSTM steps (csrc/lstm_step.cu) whenever the weights live on a GPU; the plain
         # PyTorch cells otherwise (CPU tests of the host logic, GRU models)
@@ -303,10 +306,13 @@ class BatchedStepper:
         utterance: with the batch sorted by length this removes most of the padding work."""
         enc_mod = self.asr.encoder
         n_utts = feats.shape[0]
+        for layer in getattr(enc_mod, "layers", []):
+            if hasattr(layer, "conv_split_format"):
+                layer.conv_split_format = self.vgg_split
         if n_utts == 1:
             enc, enc_len = enc_mod(feats, lens)
         elif self.split_conv and feats.is_cuda and hasattr(enc_mod, "forward_ragged_packed") and enc_mod.packed_supported():
-            # device path: split-bf16 convolutions, packed frames, persistent recurrent kernel (model.py)
+            # device path: split convolutions, packed frames, persistent recurrent kernel (model.py)
             enc_mod.split_conv = True
             enc, enc_len = enc_mod.forward_ragged_packed(feats, lens, chunk)
         elif hasattr(enc_mod, "forward_ragged"):

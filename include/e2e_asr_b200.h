@@ -287,6 +287,28 @@ int e2e_conv1_direct(const float *feat, long long feat_pitch_n, const float *wei
 int e2e_conv_bias_relu_mask_pool(const float *y_nhwc, const float *bias, const int *valid_rows, int N, int H, int W, int C,
                                  float *out_nhwc, void *stream);
 
+/* The front end in the 2-piece fp16 operand format (see e2e_lstm_split_rows_f16x2): three partial GEMM products instead
+ * of six and a third less unfolded data.  The activations are ReLU outputs of no fixed range, so the scale travels on
+ * the device: a word `amax` holds the float bits of max|x| over the rows of a layer's input that the next layer reads
+ * (x >= 0; zero it before the producing kernel runs), and
+ *   act_scale(amax) = 2^(14 - floor(log2(amax)))  (1 if amax == 0; clamped to 2^-60..2^60)
+ * puts that maximum in [2^14, 2^15).
+ *   e2e_conv1_direct_amax:              e2e_conv1_direct + max of the outputs on rows t < valid_rows[n] -> atomicMax(amax_out)
+ *   e2e_conv3x3_unfold_split_f16x2:     out fp16 [n_pixels][18*C] = [a1 | a2], a1 = fp16(s*x), a2 = fp16(s*x - a1), s = act_scale(*amax_in)
+ *   e2e_conv_bias_relu_mask_scaled:     y = relu(y * inv_w_scale / act_scale(*amax_in) + bias) (masked as above); inv_w_scale = 1/scale_w
+ *   e2e_conv_bias_relu_mask_pool_scaled of the weights' own split; max of the result -> atomicMax(amax_out) if given. */
+int e2e_conv1_direct_amax(const float *feat, long long feat_pitch_n, const float *weight, const float *bias,
+                          const int *valid_rows, int N, int L, int F, int Cin, int Cout, float *out_nhwc,
+                          unsigned *amax_out, void *stream);
+int e2e_conv3x3_unfold_split_f16x2(const float *in_nhwc, const int *valid_rows, int N, int H, int W, int C,
+                                   long long first_pixel, int n_pixels, const unsigned *amax_in, void *out_f16, void *stream);
+int e2e_conv_bias_relu_mask_scaled(float *y_nhwc, const float *bias, const int *valid_rows, int N, int H, int W, int C,
+                                   long long first_pixel, long long n_pixels, const unsigned *amax_in, float inv_w_scale,
+                                   unsigned *amax_out, void *stream);
+int e2e_conv_bias_relu_mask_pool_scaled(const float *y_nhwc, const float *bias, const int *valid_rows, int N, int H, int W, int C,
+                                        float *out_nhwc, const unsigned *amax_in, float inv_w_scale, unsigned *amax_out,
+                                        void *stream);
+
 /* Number of kernel launches issued through this library by the calling process
  * (for bench.py's gpu_launches claim). */
 long long e2e_launch_count(void);
