@@ -216,6 +216,7 @@ class BeamDecoder(nn.Module):
                 lin = self.asr.ctc_layer[0]
                 logits = F.linear(enc, lin.weight, lin.bias).contiguous()          # cuBLAS; ReLU + log-softmax fused in (1)
                 x = ops.ctc_log_softmax(logits, enc_len32, apply_relu=True)        # decode.py:94-95
+                del logits                                                         # [U,Tmax,V]: as large as x with a subword vocabulary
                 r_prev = ops.ctc_init_state(x, enc_len32)                          # decode.py:97
                 r_a = torch.empty((n_utts, t_max, beam * n_cand, 2), dtype=torch.float32, device=dev)
                 r_b = torch.empty_like(r_a)

@@ -55,15 +55,23 @@ def write_results(results, tokenizer, best_path, beam_path=None):
                 fbeam.close()
 
 
-def decode_dataset(decoder, samples, device, max_utts=4096, max_padded_frames=0):
+def decode_dataset(decoder, samples, device, max_utts=4096, max_padded_frames=0, max_bytes=None):
     """samples: sequence of (name, feat [L,D] float tensor, truth ids).  Returns the reference's
     result tuples (name, [hyp.outIndex ...], truth) in the order of ``samples``
-    (bin/test_asr.py:138-139,159-173), decoding many utterances per ``decode_batch`` call."""
+    (bin/test_asr.py:138-139,159-173), decoding many utterances per ``decode_batch`` call.
+    Batches are closed before their estimated footprint (shard.estimate_decode_bytes) exceeds ``max_bytes``
+    (default: 80 % of the device's free memory), which is what splits a subword-vocabulary set."""
+    import functools
     import torch
     from . import shard
     lengths = np.array([int(s[1].shape[0]) for s in samples], dtype=np.int64)
     out = [None] * len(samples)
-    for batch in shard.make_batches(np.arange(len(samples)), lengths, max_utts, max_padded_frames):
+    if max_bytes is None and torch.device(device).type == "cuda":
+        max_bytes = int(0.8 * torch.cuda.mem_get_info(device)[0])
+    feat_dim = int(samples[0][1].shape[1]) if len(samples) else 160
+    bytes_fn = functools.partial(shard.estimate_decode_bytes, vocab=decoder.asr.vocab_size, beam=decoder.beam_size,
+                                 n_cand=decoder.ctc_beam_size if decoder.apply_ctc else 0, feat_dim=feat_dim)
+    for batch in shard.make_batches(np.arange(len(samples)), lengths, max_utts, max_padded_frames, max_bytes, bytes_fn):
         l_max = int(lengths[batch].max())
         feats = torch.zeros(len(batch), l_max, samples[batch[0]][1].shape[1])
         for k, i in enumerate(batch):

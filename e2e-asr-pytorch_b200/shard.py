@@ -36,15 +36,40 @@ def plan_shards(lengths, world_size, max_len_ratio=0.2):
     return [np.array(s, dtype=np.int64) for s in shards]
 
 
-def make_batches(indices, lengths, max_utts=512, max_padded_frames=None):
+def estimate_decode_bytes(n_utts, l_max, vocab, beam, n_cand, feat_dim=160, enc_dim=640, att_dim=300,
+                          lm_dim=1024, lm_layers=4, encoder_chunk=128):
+    """Upper estimate of the HBM ``BeamDecoder.decode_batch`` needs at its peak for ``n_utts`` utterances padded
+    to ``l_max`` input frames (every buffer is sized by the LONGEST utterance of the batch).
+    Dominant terms: the frame-major posteriors together with the CTC logits they are made from
+    (2 x U x Tmax x Vp fp32 — 170 GB for 2620 utterances with a 10k subword vocabulary), the two prefix-state
+    buffers, the encoder output and the attention keys; the encoder's chunk temporaries are a constant."""
+    u, t = int(n_utts), (int(l_max) // 4 + 3) // 4 * 4
+    vp = (int(vocab) + 3) // 4 * 4
+    n = u * beam
+    feats = u * int(l_max) * feat_dim * 4
+    enc = u * t * enc_dim * 4 * 2                                   # padded output + the packed frames it is scattered from
+    keys = u * t * att_dim * 4 * 2                                  # proj_k output and its channel-major copy
+    post = 2 * u * t * vp * 4 + u * t * 8                           # logits + posteriors (+ blank running sum)
+    states = 2 * u * t * beam * max(1, n_cand) * 8
+    attn = 3 * n * t * 4
+    lstm = n * (lm_layers * (3 * 2 * lm_dim * 2 + 4 * lm_dim * 4) + 4 * lm_dim * 4) + 3 * n * vp * 4
+    hist = 3 * (int(l_max) // 5 + 2) * n * 4
+    chunk = min(u, encoder_chunk) * int(l_max) * 40 * 128 * 4 * 3 + (3 << 30) * 2      # VGG activations + unfolded operand + GEMM result
+    return int(1.1 * (feats + enc + keys + post + states + attn + lstm + hist + chunk))
+
+
+def make_batches(indices, lengths, max_utts=512, max_padded_frames=None, max_bytes=None, bytes_fn=None):
     """Split ``indices`` (any order) into length-sorted batches: utterances of similar length
-    share a batch so that padding and idle decode steps stay small."""
+    share a batch so that padding and idle decode steps stay small.  ``max_bytes`` with
+    ``bytes_fn(n_utts, l_max) -> bytes`` (e.g. a partial of :func:`estimate_decode_bytes`) also closes a batch
+    before its estimated footprint exceeds the budget; a single utterance is never refused."""
     lengths = np.asarray(lengths)
     idx = sorted((int(i) for i in indices), key=lambda i: (-int(lengths[i]), i))
     batches, cur = [], []
     for i in idx:
         longest = int(lengths[cur[0]]) if cur else int(lengths[i])
-        if cur and (len(cur) >= max_utts or (max_padded_frames and (len(cur) + 1) * longest > max_padded_frames)):
+        if cur and (len(cur) >= max_utts or (max_padded_frames and (len(cur) + 1) * longest > max_padded_frames)
+                    or (max_bytes and bytes_fn is not None and bytes_fn(len(cur) + 1, longest) > max_bytes)):
             batches.append(cur)
             cur = []
         cur.append(i)

@@ -186,3 +186,30 @@ def test_f16x2_split_error_budget_against_float64():
     e_fp32 = float(((x @ w.t()).double() - want).abs().max())
     assert e_repr < 0.5 * e_fp32, (e_repr, e_fp32)
     assert e_split <= 2.0 * e_fp32 + 1e-7, (e_split, e_fp32)
+
+
+def test_memory_budget_splits_a_subword_set_and_keeps_the_char_set_whole():
+    """shard.estimate_decode_bytes / make_batches(max_bytes=...): BASELINE cfg2 (char vocabulary, 2620 utterances) stays
+    ONE batch under a B200's 180 GB (it is measured as one), cfg3 (10k subword vocabulary: 86 GB of
+    posteriors plus as many logits at Tmax = 825) is split, every utterance lands in exactly one batch, and a single
+    utterance is never refused."""
+    import functools
+    from e2e_asr_pytorch_b200 import shard, synth
+    lengths = synth.devclean_lengths(2620, seed=2)
+    budget = int(0.8 * 178e9)
+    char = functools.partial(shard.estimate_decode_bytes, vocab=31, beam=8, n_cand=12)
+    sub = functools.partial(shard.estimate_decode_bytes, vocab=10000, beam=8, n_cand=12)
+    whole = char(2620, int(lengths.max()))
+    assert 20e9 < whole < budget, whole
+    assert sub(2620, int(lengths.max())) > 178e9
+    one = shard.make_batches(np.arange(2620), lengths, 4096, 0, budget, char)
+    assert len(one) == 1 and len(one[0]) == 2620
+    parts = shard.make_batches(np.arange(2620), lengths, 4096, 0, budget, sub)
+    assert len(parts) >= 2
+    assert sorted(i for b in parts for i in b) == list(range(2620))
+    for b in parts:
+        assert sub(len(b), int(lengths[b].max())) <= budget
+        assert all(lengths[b[k]] >= lengths[b[k + 1]] for k in range(len(b) - 1))       # longest first inside a batch
+    tiny = shard.make_batches(np.arange(3), lengths[:3], 4096, 0, 1, sub)               # absurd budget: one utterance per batch
+    assert [len(b) for b in tiny] == [1, 1, 1]
+    assert char(10, 800) < char(11, 800) < char(11, 1600)                                # monotone in both arguments
