@@ -213,3 +213,23 @@ def test_memory_budget_splits_a_subword_set_and_keeps_the_char_set_whole():
     tiny = shard.make_batches(np.arange(3), lengths[:3], 4096, 0, 1, sub)               # absurd budget: one utterance per batch
     assert [len(b) for b in tiny] == [1, 1, 1]
     assert char(10, 800) < char(11, 800) < char(11, 1600)                                # monotone in both arguments
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the arm the driver times next to ours) on a tiny bounded sample: one JSON line with the
+    contract's keys, no GPU needed, rank != 0 exits silently."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--cpu-sample", "2", "--cpu-frames", "40", "--cpu-procs", "2"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "utts/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "utts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 2 and d["gpu_launches"] == 0
+    assert "median" not in d["cpu_baseline"]["sample"]                      # 40 frames is not the workload's median
+    quiet = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
