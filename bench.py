@@ -156,6 +156,8 @@ def run_b200(args):
         dec.lm_split = args.lm_split
     if args.vgg_split:
         dec.vgg_split = args.vgg_split
+    if args.prefix_math:
+        dec.prefix_math = args.prefix_math
     lengths = workload_lengths(world, args.n_utts)
     n_total = len(lengths)
     shards = shard.plan_shards(lengths, world, MAX_RATIO)
@@ -243,7 +245,7 @@ def run_b200(args):
         "config": {"workload": "cfg2: char V=31 VGG+BLSTM CTC-attention (librispeech_asr.yaml dims, vgg=1) + 4x1024 RNNLM, "
                                "beam 8, ctc 0.5, lm 0.5, max_len_ratio 0.2, %d utts/GPU dev-clean-like lengths, random init" % args.n_utts,
                    "utterances": n_total, "batches_per_gpu": len(batches), "max_utts_per_batch": args.max_utts,
-                   "prefix_fast_math": bool(args.fast_math), "skip_dead_rows": not args.write_dead_rows,
+                   "prefix_fast_math": bool(args.fast_math), "prefix_math": "mufu" if args.fast_math else dec.prefix_math, "skip_dead_rows": not args.write_dead_rows,
                    "lm_gemm_operands": dec.lm_split, "vgg_gemm_operands": dec.vgg_split,
                    "l2": "inputs (%.1f GB features + GB-scale prefix states per batch) exceed the 126 MB L2; no flush needed" % (in_bytes / 1e9),
                    "parallelism": "utterance shards x%d, one all-gather of N-best" % world},
@@ -377,6 +379,8 @@ def main():
                     help="operand format of the RNNLM's recurrent GEMMs (default: the decoder's, bf16x3)")
     ap.add_argument("--vgg-split", default="", choices=["", "bf16x3", "fp16x2"],
                     help="operand format of the VGG convolution GEMMs (default: the decoder's, bf16x3)")
+    ap.add_argument("--prefix-math", default="", choices=["", "lut", "poly", "poly_estrin"],
+                    help="log-add-exp evaluator of the prefix-score kernel (default: the decoder's, lut)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0)

@@ -20,6 +20,8 @@ PREFIX_SKIP_DEAD_ROWS = 2
 PREFIX_FAST_MATH = 4
 PREFIX_LIBM_MATH = 8
 PREFIX_ROW_COPIES = 16
+PREFIX_POLY_MATH = 32
+PREFIX_POLY_ESTRIN = 64
 BEAM_USE_CTC = 1
 BEAM_USE_LM = 2
 

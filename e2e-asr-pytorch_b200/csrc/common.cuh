@@ -24,8 +24,14 @@ void count_launch(int n = 1);
 //              within one fp32 rounding of the exact value, bit-equal to glibc's log1pf(expf(d))
 //              for ~3/4 of inputs, branch free, ~23 instructions;
 //   kMathMufu  MUFU.EX2 + MUFU.LG2 (absolute error ~3e-7), ~8 instructions;
-//   kMathLibm  CUDA expf + log1pf (branchy, ~55 instructions) — kept as a cross-check.
-enum { kMathLut = 0, kMathMufu = 1, kMathLibm = 2 };
+//   kMathLibm  CUDA expf + log1pf (branchy, ~55 instructions) — kept as a cross-check;
+//   kMathPoly  MUFU.EX2 + a degree-8 polynomial in e = exp(-|x-y|): softplus = e*P(e) (tools/gen_softplus_poly.py),
+//              no table, no tail case, ~14 instructions (kMathPolyEstrin: the same polynomial evaluated pairwise,
+//              3 more instructions, half the dependent FMA chain).  The polynomial is good to 3.3e-8; in emulated
+//              fp32 the whole recursion stays within 1 ulp of the oracle (tools/emulate_prefix_math.py).  Opt-in
+//              until measured on the GPU.
+enum { kMathLut = 0, kMathMufu = 1, kMathLibm = 2, kMathPoly = 3, kMathPolyEstrin = 4 };
+#include "softplus_poly.inc"
 
 constexpr int kLutNodes = 65;     // d in [-4, 0], spacing 1/16
 constexpr int kLutCopies = 8;     // one copy per lane of a quarter warp: LDS.128 never bank-conflicts
@@ -83,6 +89,31 @@ __device__ __forceinline__ uint32_t softplus_lut_adj(const float4 *lut)
     return smem_u32(lut) - (0x4B400000u << 7);
 }
 
+// ad = |a-b| >= 0; softplus(-ad) = log1p(e) = e*P(e) with e = exp(-ad)
+template <bool kEstrin>
+__device__ __forceinline__ float softplus_poly(float ad)
+{
+    const float e = ex2_approx(ad * -1.4426950408889634f);
+    float p;
+    if (!kEstrin) {
+        p = fmaf(kSoftplusPolyC8, e, kSoftplusPolyC7);
+        p = fmaf(p, e, kSoftplusPolyC6);
+        p = fmaf(p, e, kSoftplusPolyC5);
+        p = fmaf(p, e, kSoftplusPolyC4);
+        p = fmaf(p, e, kSoftplusPolyC3);
+        p = fmaf(p, e, kSoftplusPolyC2);
+        p = fmaf(p, e, kSoftplusPolyC1);
+        p = fmaf(p, e, kSoftplusPolyC0);
+    } else {
+        const float e2 = e * e, e4 = e2 * e2;
+        const float p01 = fmaf(kSoftplusPolyC1, e, kSoftplusPolyC0), p23 = fmaf(kSoftplusPolyC3, e, kSoftplusPolyC2);
+        const float p45 = fmaf(kSoftplusPolyC5, e, kSoftplusPolyC4), p67 = fmaf(kSoftplusPolyC7, e, kSoftplusPolyC6);
+        const float lo = fmaf(p23, e2, p01), hi = fmaf(p67, e2, p45);
+        p = fmaf(fmaf(kSoftplusPolyC8, e4, hi), e4, lo);
+    }
+    return e * p;
+}
+
 template <int kMath>
 __device__ __forceinline__ float logaddexp(float a, float b, uint32_t lut)
 {
@@ -91,6 +122,8 @@ __device__ __forceinline__ float logaddexp(float a, float b, uint32_t lut)
     float l;
     if (kMath == kMathLut) {
         l = softplus_lut(ad, lut);
+    } else if (kMath == kMathPoly || kMath == kMathPolyEstrin) {
+        l = softplus_poly<kMath == kMathPolyEstrin>(ad);
     } else if (kMath == kMathMufu) {
         l = lg2_approx(1.0f + ex2_approx(ad * -1.4426950408889634f)) * E2E_LN2F;
     } else {

@@ -50,6 +50,8 @@ __host__ __device__ constexpr int phi_pitch(int tile) { return 2 * tile + 2; }  
 constexpr int kMaxRowFloats = 256;   // rows variant up to 1 KB per posterior row
 constexpr int kMaxLanes = 128;       // lanes (= threads) per CTA
 constexpr int kLutBytes = kLutNodes * kLutCopies * 16;
+// the polynomial log-add-exp needs no table: its kernels start their shared-memory layout at offset 0
+__host__ __device__ constexpr int lut_bytes(int math) { return (math == kMathPoly || math == kMathPolyEstrin) ? 0 : kLutBytes; }
 
 struct PrefixParams {
     const float *x; int Tmax, U, Vp, V;
@@ -113,7 +115,7 @@ prefix_score_kernel(const PrefixParams p, const __grid_constant__ CUtensorMap tm
 
     // ---- shared memory: LUT replicas | x tiles | phi tiles (x2) | raw parent states | s_plane[H] | s_red[2] | mbarriers[2]
     const int H = p.hyps_per_cta;
-    const size_t xs_off = kLutBytes;
+    const size_t xs_off = lut_bytes(kMath);
     const size_t phis_off = xs_off + prefix_xs_bytes(kGather, nl, Vp, kT);
     const size_t stage_off = phis_off + prefix_phis_bytes(H, kT);
     const size_t misc_off = stage_off + prefix_stage_bytes(H, kT);
@@ -313,9 +315,9 @@ prefix_score_kernel(const PrefixParams p, const __grid_constant__ CUtensorMap tm
     }
 }
 
-static size_t prefix_smem_bytes(bool gather, int lanes, int Vp, int H, int tile)
+static size_t prefix_smem_bytes(bool gather, int lanes, int Vp, int H, int tile, int math)
 {
-    size_t b = kLutBytes + prefix_xs_bytes(gather, lanes, Vp, tile) + prefix_phis_bytes(H, tile) + prefix_stage_bytes(H, tile);
+    size_t b = lut_bytes(math) + prefix_xs_bytes(gather, lanes, Vp, tile) + prefix_phis_bytes(H, tile) + prefix_stage_bytes(H, tile);
     b = ((b + (size_t)(H + 2) * 4 + 7) & ~(size_t)7) + 16;
     return (b + 15) & ~(size_t)15;
 }
@@ -407,7 +409,9 @@ extern "C" int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int
     if (grid > 0x7fffffffLL) return set_error(E2E_ERR_UNSUPPORTED, "e2e_ctc_prefix_score: grid too large");
 
     const bool gather = Vp > kMaxRowFloats;
-    const int math = (flags & E2E_PREFIX_FAST_MATH) ? kMathMufu : ((flags & E2E_PREFIX_LIBM_MATH) ? kMathLibm : kMathLut);
+    const int math = (flags & E2E_PREFIX_FAST_MATH) ? kMathMufu
+                   : (flags & E2E_PREFIX_LIBM_MATH) ? kMathLibm
+                   : (flags & E2E_PREFIX_POLY_MATH) ? ((flags & E2E_PREFIX_POLY_ESTRIN) ? kMathPolyEstrin : kMathPoly) : kMathLut;
     const bool fixed = !gather && Vp == 32 && LU == 96;      // char vocabulary, beam 8 (BASELINE cfg2)
     const bool use_map = !gather && !(flags & E2E_PREFIX_ROW_COPIES);
     // Tile size by launch size (only the default-math tensor-map kernels are built with the small tile)
@@ -415,9 +419,10 @@ extern "C" int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int
         const char *e = getenv("E2E_PREFIX_SMALL_TILE_FROM");    // tuning knob: CTAs from which the 16-frame tile is used
         return e ? atoll(e) : 1000LL;
     }();
-    const bool big_launch = use_map && math == kMathLut && grid >= small_tile_from;
+    const bool tiled_math = math == kMathLut || math == kMathPoly || math == kMathPolyEstrin;      // built with both tile sizes
+    const bool big_launch = use_map && tiled_math && grid >= small_tile_from;
     const int tile = big_launch ? kTileBig : kTileSmall;
-    const size_t smem = prefix_smem_bytes(gather, nl, Vp, p.hyps_per_cta, tile);
+    const size_t smem = prefix_smem_bytes(gather, nl, Vp, p.hyps_per_cta, tile, math);
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
     if (use_map) {
@@ -428,13 +433,23 @@ extern "C" int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int
     PrefixKernel kern;
     if (gather)
         kern = math == kMathLut ? prefix_score_kernel<true, kMathLut, 0, 0, false, TS>
-                                : (math == kMathMufu ? prefix_score_kernel<true, kMathMufu, 0, 0, false, TS> : prefix_score_kernel<true, kMathLibm, 0, 0, false, TS>);
+             : math == kMathMufu ? prefix_score_kernel<true, kMathMufu, 0, 0, false, TS>
+             : math == kMathLibm ? prefix_score_kernel<true, kMathLibm, 0, 0, false, TS>
+             : math == kMathPoly ? prefix_score_kernel<true, kMathPoly, 0, 0, false, TS> : prefix_score_kernel<true, kMathPolyEstrin, 0, 0, false, TS>;
     else if (!use_map)
         kern = math == kMathLut ? prefix_score_kernel<false, kMathLut, 0, 0, false, TS>
-                                : (math == kMathMufu ? prefix_score_kernel<false, kMathMufu, 0, 0, false, TS> : prefix_score_kernel<false, kMathLibm, 0, 0, false, TS>);
+             : math == kMathMufu ? prefix_score_kernel<false, kMathMufu, 0, 0, false, TS>
+             : math == kMathLibm ? prefix_score_kernel<false, kMathLibm, 0, 0, false, TS>
+             : math == kMathPoly ? prefix_score_kernel<false, kMathPoly, 0, 0, false, TS> : prefix_score_kernel<false, kMathPolyEstrin, 0, 0, false, TS>;
     else if (math == kMathLut) {
         if (fixed) kern = big_launch ? prefix_score_kernel<false, kMathLut, 32, 96, true, TB> : prefix_score_kernel<false, kMathLut, 32, 96, true, TS>;
         else kern = big_launch ? prefix_score_kernel<false, kMathLut, 0, 0, true, TB> : prefix_score_kernel<false, kMathLut, 0, 0, true, TS>;
+    } else if (math == kMathPoly) {
+        if (fixed) kern = big_launch ? prefix_score_kernel<false, kMathPoly, 32, 96, true, TB> : prefix_score_kernel<false, kMathPoly, 32, 96, true, TS>;
+        else kern = big_launch ? prefix_score_kernel<false, kMathPoly, 0, 0, true, TB> : prefix_score_kernel<false, kMathPoly, 0, 0, true, TS>;
+    } else if (math == kMathPolyEstrin) {
+        if (fixed) kern = big_launch ? prefix_score_kernel<false, kMathPolyEstrin, 32, 96, true, TB> : prefix_score_kernel<false, kMathPolyEstrin, 32, 96, true, TS>;
+        else kern = big_launch ? prefix_score_kernel<false, kMathPolyEstrin, 0, 0, true, TB> : prefix_score_kernel<false, kMathPolyEstrin, 0, 0, true, TS>;
     } else
         kern = math == kMathMufu ? prefix_score_kernel<false, kMathMufu, 0, 0, true, TS> : prefix_score_kernel<false, kMathLibm, 0, 0, true, TS>;
     if (smem > 48 * 1024) {

@@ -123,6 +123,9 @@ class BeamDecoder(nn.Module):
 
         # knobs of the device path (not part of the reference interface)
         self.fast_math = False          # MUFU log-add-exp in the prefix-score kernel
+        # log-add-exp evaluator of the prefix-score kernel: "lut" (default, table), "poly" / "poly_estrin" (MUFU.EX2 + degree-8
+        # polynomial: 23 % fewer instructions per candidate-frame, csrc/common.cuh; an experiment until measured on the GPU)
+        self.prefix_math = os.environ.get("E2E_PREFIX_MATH", "lut")
         self.skip_dead_rows = True      # do not write state rows t < len(prefix) nobody reads back
         self.split_gemm = True          # fp32-accurate 3-way bf16 split of the recurrent GEMMs (stepper.py)
         # operand format of the RNNLM's recurrent GEMMs: "bf16x3" (six partial products) or "fp16x2" (three; every
@@ -221,6 +224,8 @@ class BeamDecoder(nn.Module):
                 r_a = torch.empty((n_utts, t_max, beam * n_cand, 2), dtype=torch.float32, device=dev)
                 r_b = torch.empty_like(r_a)
             pflags = (L.PREFIX_FAST_MATH if self.fast_math else 0) | (L.PREFIX_SKIP_DEAD_ROWS if self.skip_dead_rows else 0)
+            if not self.fast_math:
+                pflags |= {"lut": 0, "poly": L.PREFIX_POLY_MATH, "poly_estrin": L.PREFIX_POLY_MATH | L.PREFIX_POLY_ESTRIN}[self.prefix_math]
             if self.profile_prefix and self.apply_ctc:
                 t_np, s_np = enc_len.cpu().numpy().astype(np.int64), max_len.numpy().astype(np.int64)
 

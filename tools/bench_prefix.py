@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--plen", type=int, default=1)
     ap.add_argument("--fast", type=int, default=0)
     ap.add_argument("--libm", type=int, default=0)
+    ap.add_argument("--poly", type=int, default=0, help="1: MUFU.EX2 + polynomial log-add-exp (Horner), 2: the same, pairwise (Estrin)")
     ap.add_argument("--skip-dead", type=int, default=0)
     ap.add_argument("--ragged", type=int, default=0)
     a = ap.parse_args()
@@ -53,6 +54,8 @@ def main():
     psi = torch.empty((U * B, C), device=dev)
     status = torch.zeros(U, dtype=torch.int32, device=dev)
     flags = (L.PREFIX_FAST_MATH if a.fast else 0) | (L.PREFIX_LIBM_MATH if a.libm else 0) | (L.PREFIX_SKIP_DEAD_ROWS if a.skip_dead else 0)
+    if a.poly and not (a.fast or a.libm):
+        flags |= L.PREFIX_POLY_MATH | (L.PREFIX_POLY_ESTRIN if a.poly == 2 else 0)
     # first launch from the empty prefix fills bufs[0] with valid states
     ops.ctc_prefix_score(x, V, enc_len, r0, torch.zeros_like(lane), last, torch.zeros_like(plen),
                          torch.ones_like(n_live), cand, B, C, 0, psi=psi, r_out=bufs[0], status=status)
@@ -85,7 +88,7 @@ def main():
         pass
     gbs = units * bpu / (ms.mean() * 1e-3) / 1e9
     print(json.dumps({"kernel": "prefix_score", "utts": U, "frames": T, "vocab": V, "beam": B, "cand": C, "plen": a.plen,
-                      "math": "mufu" if a.fast else ("libm" if a.libm else "lut"), "skip_dead_rows": a.skip_dead, "ms_mean": float(ms.mean()), "ms_min": float(ms.min()),
+                      "math": "mufu" if a.fast else ("libm" if a.libm else (["lut", "poly", "poly_estrin"][a.poly])), "skip_dead_rows": a.skip_dead, "ms_mean": float(ms.mean()), "ms_min": float(ms.min()),
                       "cand_frames": units, "cand_frames_per_s": units / (ms.mean() * 1e-3), "bytes_per_cand_frame": bpu,
                       "algorithmic_GBps": gbs, "frac_of_measured_hbm_peak": gbs / peak, "status": int(status.sum().item()),
                       "state_buffer_MB": bufs[0].numel() * 4 / 1e6}))
