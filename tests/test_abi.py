@@ -44,6 +44,19 @@ def test_argument_validation_needs_no_device():
     assert lib.e2e_ctc_init_state(None, 1, 1, 32, None, None, None) == -1
     assert lib.e2e_beam_candidates(None, 31, 1, 1, 31, 3, None, None, None, None) == -1
     assert lib.e2e_beam_finalize(0, 1, *([None] * 11), 1, *([None] * 5), 1, None) == -1
+    # the operand-format entry points: null pointers, geometry and scales are refused before any launch
+    fake = ctypes.c_void_p(256)                      # a non-null, aligned "device pointer" that is never dereferenced
+    assert lib.e2e_lstm_split_rows(None, 8, None, 1, 8, None, 24, 8, 0, None) == -1
+    assert lib.e2e_lstm_split_rows(fake, 8, None, 1, 8, fake, 16, 8, 0, None) == -1             # bf16 needs a pitch of 3K
+    assert lib.e2e_lstm_split_rows_f16x2(fake, 8, None, 1, 8, fake, 16, 8, 0, 3.0, None) == -1   # scale not a power of two
+    assert b"power of two" in lib.e2e_last_error()
+    assert lib.e2e_lstm_split_rows_f16x2(fake, 8, None, 1, 8, fake, 8, 8, 0, 2.0, None) == -1    # fp16 needs a pitch of 2K
+    assert lib.e2e_lstm_cell_f16x2(fake, 16, 0.0, fake, None, None, fake, None, 1, 4, fake, fake, None, 0, 0, 0, 1.0, None) == -1
+    assert lib.e2e_conv3x3_unfold_split_f16x2(fake, fake, 1, 4, 4, 4, 0, 16, None, fake, None) == -1   # no scale word
+    assert lib.e2e_conv_bias_relu_mask_scaled(fake, fake, fake, 1, 4, 4, 4, 0, 16, fake, 0.0, None, None) == -1
+    assert b"inv_w_scale" in lib.e2e_last_error()
+    assert lib.e2e_conv_bias_relu_mask_pool_scaled(fake, fake, fake, 1, 4, 4, 4, fake, None, 1.0, None, None) == -1
+    assert lib.e2e_conv1_direct_amax(fake, 640, fake, fake, fake, 1, 4, 40, 4, 128, fake, None, None) == -1
 
 
 def test_sass_uses_the_tma_engine_and_no_legacy_tensor_path():

@@ -1,0 +1,22 @@
+#!/bin/bash
+# First GPU call of the next round: everything round 1 prepared without GPU minutes, in one go (~4 min of box time).
+#   /usr/local/graft/bin/gpurun --timeout 420 -- 'bash tools/round2_first_call.sh'
+# Results land in gpurun_out/r2_*.log; nothing here changes a default.
+set -u
+mkdir -p gpurun_out
+# 1. the whole GPU suite including the tests that are still waiting for their first run (poly log-add-exp)
+E2E_UNVALIDATED_TESTS=1 timeout 170 python -m pytest tests -m gpu -q --timeout 90 -rA > gpurun_out/r2_pytest_all.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r2_pytest_all.log
+# 2. prefix-score kernel, stand-alone: table vs polynomial log-add-exp on the three launch shapes of DESIGN.md §6
+for poly in 0 1 2; do
+  timeout 40 python tools/bench_prefix.py --utts 2620 --poly $poly
+  timeout 40 python tools/bench_prefix.py --utts 2620 --plen 60 --skip-dead 1 --poly $poly
+  timeout 40 python tools/bench_prefix.py --utts 64 --frames 825 --poly $poly
+  timeout 40 python tools/bench_prefix.py --utts 256 --frames 875 --beam 16 --poly $poly
+done > gpurun_out/r2_prefix_math_micro.jsonl 2> gpurun_out/r2_prefix_math_micro.err
+# 3. the decode with the polynomial evaluator (roofline.frac in-decode) next to the default
+timeout 90 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_default.log 2> gpurun_out/r2_bench_default.err
+timeout 90 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --prefix-math poly > gpurun_out/r2_bench_poly.log 2> gpurun_out/r2_bench_poly.err
+tail -3 gpurun_out/r2_pytest_all.log
+cat gpurun_out/r2_prefix_math_micro.jsonl | cut -c1-260
+cut -c1-200 gpurun_out/r2_bench_default.log gpurun_out/r2_bench_poly.log
