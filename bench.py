@@ -289,7 +289,6 @@ def _cpu_worker(job):
         asr, lm = synth.build_asr(VOCAB, seed=0), synth.build_lm(VOCAB, seed=1)
         _CPU_MODELS = (asr, lm)
     feat = synth.utterance(uid, n)[None]
-    trace = []
     t0 = time.time()
     with th.no_grad():
         nb = BO.decode_utterance(asr, feat, th.LongTensor([n]), BEAM, MIN_RATIO, MAX_RATIO, lm=lm,
