@@ -34,19 +34,35 @@ def stale():
 
 
 def build(force=False, verbose=False):
-    """Compile the extension if missing or older than its sources.  Returns the path."""
+    """Compile the extension if missing or older than its sources.  Returns the path.
+    The translation units are compiled concurrently (one nvcc per .cu), then linked."""
     if not force and not stale():
         return LIB_PATH
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libe2e_asr_b200.so")
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
-    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
-    if verbose:
-        print(proc.stderr)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    with tempfile.TemporaryDirectory(prefix="e2e_build_") as tmp:
+        def compile_one(src):
+            obj = os.path.join(tmp, src.replace(".cu", ".o"))
+            proc = subprocess.run([nvcc] + compile_flags + ["-c", "-o", obj, src], cwd=CSRC, capture_output=True, text=True)
+            return src, obj, proc
+        with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+            done = list(pool.map(compile_one, SOURCES))
+        failed = [(src, proc) for src, _, proc in done if proc.returncode != 0]
+        if failed:
+            raise RuntimeError("nvcc failed:\n" + "\n".join(src + ":\n" + proc.stdout + proc.stderr for src, proc in failed))
+        if verbose:
+            for src, _, proc in done:
+                print(proc.stderr)
+        out_tmp = LIB_PATH + ".tmp%d" % os.getpid()
+        link = subprocess.run([nvcc] + NVCC_FLAGS + ["-o", out_tmp] + [obj for _, obj, _ in done], cwd=CSRC, capture_output=True, text=True)
+        if link.returncode != 0:
+            raise RuntimeError("nvcc link failed:\n" + link.stdout + link.stderr)
+        os.replace(out_tmp, LIB_PATH)                      # atomic: a concurrent loader never sees a half-written library
     return LIB_PATH
 
 
