@@ -168,11 +168,17 @@ def run_b200(args):
     host = [make_features(b, lengths, pin=True) for b in batches]            # pinned host buffers
     resident = [(f.to(dev), l.to(dev)) for f, l in host]                      # HBM-resident copies
     h2d_bytes = sum(f.numel() * 4 + l.numel() * 8 for f, l in host)
+    if args.ragged_h2d:                                                        # only the valid frames are copied
+        h2d_bytes = sum(int(l.sum()) * f.shape[2] * 4 + l.numel() * 8 for f, l in host)
     in_bytes = sum(f.numel() * 4 for f, _ in resident)
 
     def one_pass(from_host):
         parts, ids = [], []
         for b, hb, rb in zip(batches, host, resident):
+            if from_host and args.ragged_h2d:
+                parts.append(dec.decode_batch_from_host(hb[0], hb[1], dev, return_arrays=True))   # valid frames only cross the bus
+                ids.extend(b)
+                continue
             if from_host:
                 feat, fl = hb[0].to(dev, non_blocking=True), hb[1].to(dev, non_blocking=True)
             else:
@@ -246,6 +252,7 @@ def run_b200(args):
                                "beam 8, ctc 0.5, lm 0.5, max_len_ratio 0.2, %d utts/GPU dev-clean-like lengths, random init" % args.n_utts,
                    "utterances": n_total, "batches_per_gpu": len(batches), "max_utts_per_batch": args.max_utts,
                    "prefix_fast_math": bool(args.fast_math), "prefix_math": "mufu" if args.fast_math else dec.prefix_math, "skip_dead_rows": not args.write_dead_rows,
+                   "h2d": "valid frames only, one copy per utterance" if args.ragged_h2d else "padded [U,Lmax,D] tensor, one copy",
                    "lm_gemm_operands": dec.lm_split, "vgg_gemm_operands": dec.vgg_split,
                    "l2": "inputs (%.1f GB features + GB-scale prefix states per batch) exceed the 126 MB L2; no flush needed" % (in_bytes / 1e9),
                    "parallelism": "utterance shards x%d, one all-gather of N-best" % world},
@@ -380,6 +387,8 @@ def main():
                     help="operand format of the VGG convolution GEMMs (default: the decoder's, bf16x3)")
     ap.add_argument("--prefix-math", default="", choices=["", "lut", "poly", "poly_estrin"],
                     help="log-add-exp evaluator of the prefix-score kernel (default: the decoder's, lut)")
+    ap.add_argument("--ragged-h2d", action="store_true",
+                    help="e2e leg: copy only the valid frames of every utterance (BeamDecoder.decode_batch_from_host)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0)
