@@ -17,9 +17,10 @@ done > gpurun_out/r2_prefix_math_micro.jsonl 2> gpurun_out/r2_prefix_math_micro.
 # 3. the decode with the polynomial evaluator (roofline.frac in-decode) next to the default
 timeout 90 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_default.log 2> gpurun_out/r2_bench_default.err
 timeout 90 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --prefix-math poly > gpurun_out/r2_bench_poly.log 2> gpurun_out/r2_bench_poly.err
+timeout 90 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --ragged-h2d > gpurun_out/r2_bench_ragged_h2d.log 2> gpurun_out/r2_bench_ragged_h2d.err
 # 4. the two BASELINE configurations the bench does not run (one pass each; cfg3 in memory-budgeted batches)
 timeout 150 python tools/bench_config.py --cfg 4 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r2_bench_cfg4.log 2> gpurun_out/r2_bench_cfg4.err
 timeout 240 python tools/bench_config.py --cfg 3 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r2_bench_cfg3.log 2> gpurun_out/r2_bench_cfg3.err
 tail -3 gpurun_out/r2_pytest_all.log
 cat gpurun_out/r2_prefix_math_micro.jsonl | cut -c1-260
-cut -c1-200 gpurun_out/r2_bench_default.log gpurun_out/r2_bench_poly.log gpurun_out/r2_bench_cfg4.log gpurun_out/r2_bench_cfg3.log
+cut -c1-200 gpurun_out/r2_bench_default.log gpurun_out/r2_bench_poly.log gpurun_out/r2_bench_ragged_h2d.log gpurun_out/r2_bench_cfg4.log gpurun_out/r2_bench_cfg3.log
