@@ -56,6 +56,13 @@ struct AttFullParams {
 #ifndef E2E_AF_MINBLOCKS
 #define E2E_AF_MINBLOCKS 3
 #endif
+// Value rows in flight per thread in the context product of kernel B (one 16-byte load each).  The product walks an
+// utterance's value rows once, sequentially per output column, so it lives on memory-level parallelism: round 1
+// measured it at ~4x its HBM floor with 4.  Tuning knob for tools/sweep_prefix_variants.py (the accumulation order,
+// hence the result, does not depend on it).
+#ifndef E2E_AF_CTX_FRAMES
+#define E2E_AF_CTX_FRAMES 4
+#endif
 template <int NB, int KP>
 __global__ void __launch_bounds__(kAfThreads, E2E_AF_MINBLOCKS)
 attention_energy_kernel(const AttFullParams p)
@@ -218,25 +225,29 @@ attention_softmax_context_kernel(const AttFullParams p)
                     for (int i = 0; i < 4; ++i) acc[b][i] = 0.0f;
                 const float *vp = vbase + e;
                 int t = 0;
-                for (; t + 4 <= Tu; t += 4) {
-                    float4 v[4];
+                constexpr int kF = E2E_AF_CTX_FRAMES;                        // multiple of 4
+                for (; t + kF <= Tu; t += kF) {
+                    float4 v[kF];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const float4 *>(vp + (size_t)(t + q) * p.E));
+                    for (int q = 0; q < kF; ++q) v[q] = __ldg(reinterpret_cast<const float4 *>(vp + (size_t)(t + q) * p.E));
 #pragma unroll
                     for (int b = 0; b < kBC; ++b) {
                         if (b < nb) {
-                            float a[4];
-                            if (t_vec) {                                     // broadcast load (L1), 16 bytes when rows are aligned
-                                const float4 a4 = *reinterpret_cast<const float4 *>(ar + (size_t)b * T + t);
-                                a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
-                            } else {
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) a[q] = ar[(size_t)b * T + t + q];
-                            }
+                            for (int q0 = 0; q0 < kF; q0 += 4) {
+                                float a[4];
+                                if (t_vec) {                                 // broadcast load (L1), 16 bytes when rows are aligned
+                                    const float4 a4 = *reinterpret_cast<const float4 *>(ar + (size_t)b * T + t + q0);
+                                    a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
+                                } else {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                acc[b][0] = fmaf(a[q], v[q].x, acc[b][0]); acc[b][1] = fmaf(a[q], v[q].y, acc[b][1]);
-                                acc[b][2] = fmaf(a[q], v[q].z, acc[b][2]); acc[b][3] = fmaf(a[q], v[q].w, acc[b][3]);
+                                    for (int q = 0; q < 4; ++q) a[q] = ar[(size_t)b * T + t + q0 + q];
+                                }
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    acc[b][0] = fmaf(a[q], v[q0 + q].x, acc[b][0]); acc[b][1] = fmaf(a[q], v[q0 + q].y, acc[b][1]);
+                                    acc[b][2] = fmaf(a[q], v[q0 + q].z, acc[b][2]); acc[b][3] = fmaf(a[q], v[q0 + q].w, acc[b][3]);
+                                }
                             }
                         }
                     }

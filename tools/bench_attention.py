@@ -1,6 +1,9 @@
 """Micro-benchmark of the fused location-aware attention step (the command ncu profiles).
 
-    python tools/bench_attention.py [--utts 1024] [--frames 180] [--beam 8] [--ragged 1] [--nb 0]
+    python tools/bench_attention.py [--utts 1024] [--frames 180] [--beam 8] [--ragged 1] [--nb 0] [--kernels 1]
+
+``--kernels 1`` adds the device time of each of the two kernels (CUPTI via torch.profiler) and the context
+product's HBM floor (one pass over the value rows of the live frames).
 """
 import argparse
 import json
@@ -22,6 +25,7 @@ def main():
     ap.add_argument("--ragged", type=int, default=0)
     ap.add_argument("--nb", type=int, default=0)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--kernels", type=int, default=0)
     a = ap.parse_args()
     from e2e_asr_pytorch_b200 import ops
     dev = torch.device("cuda:0")
@@ -56,7 +60,19 @@ def main():
     torch.cuda.synchronize()
     ms = sum(x.elapsed_time(y) for x, y in evs) / len(evs)
     frames = float(enc_len.sum().item()) * B
-    print(json.dumps({"kernel": "attention_loc_full", "utts": U, "frames": T, "beam": B, "ragged": a.ragged, "nb": a.nb, "ms": ms,
+    per_kernel = {}
+    if a.kernels:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(a.steps):
+                run()
+            torch.cuda.synchronize()
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA and "attention" in ev.name:
+                key = "energy_us" if "energy" in ev.name else "softmax_context_us"
+                per_kernel[key] = per_kernel.get(key, 0.0) + ev.device_time / a.steps
+        per_kernel["context_hbm_floor_us"] = float(enc_len.sum().item()) * E * 4 / 6496.8e9 * 1e6
+    print(json.dumps({**per_kernel, "kernel": "attention_loc_full", "utts": U, "frames": T, "beam": B, "ragged": a.ragged, "nb": a.nb, "ms": ms,
                       "hyp_frames": frames, "hyp_frame_channels_per_s": frames * A / (ms * 1e-3),
                       "mufu_bound_frac": frames * A * 4 / (ms * 1e-3) / (148 * 16 * 1.9e9)}))
 
