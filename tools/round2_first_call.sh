@@ -14,6 +14,13 @@ for poly in 0 1 2; do
   timeout 40 python tools/bench_prefix.py --utts 64 --frames 825 --poly $poly
   timeout 40 python tools/bench_prefix.py --utts 256 --frames 875 --beam 16 --poly $poly
 done > gpurun_out/r2_prefix_math_micro.jsonl 2> gpurun_out/r2_prefix_math_micro.err
+# 2b. attention context product: direct (default) vs bulk-copy staged value tiles; parity of the staged variant first
+E2E_AF_CTX_STAGED=1 timeout 120 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_decode.py -m gpu -q -k "attention or decode_batch_matches or order_independent" > gpurun_out/r2_pytest_ctx_staged.log 2>&1
+for staged in 0 1; do
+  E2E_AF_CTX_STAGED=$staged timeout 40 python tools/bench_attention.py --utts 2620 --frames 180 --ragged 1 --kernels 1
+  E2E_AF_CTX_STAGED=$staged timeout 40 python tools/bench_attention.py --utts 600 --frames 824 --ragged 1 --kernels 1
+done > gpurun_out/r2_attention_ctx_staged.jsonl 2> gpurun_out/r2_attention_ctx_staged.err
+E2E_AF_CTX_STAGED=1 timeout 90 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_ctx_staged.log 2> gpurun_out/r2_bench_ctx_staged.err
 # 3. the decode with the polynomial evaluator (roofline.frac in-decode) next to the default
 timeout 90 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_default.log 2> gpurun_out/r2_bench_default.err
 timeout 90 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --prefix-math poly > gpurun_out/r2_bench_poly.log 2> gpurun_out/r2_bench_poly.err
@@ -21,6 +28,6 @@ timeout 90 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --ragged-h2d >
 # 4. the two BASELINE configurations the bench does not run (one pass each; cfg3 in memory-budgeted batches)
 timeout 150 python tools/bench_config.py --cfg 4 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r2_bench_cfg4.log 2> gpurun_out/r2_bench_cfg4.err
 timeout 240 python tools/bench_config.py --cfg 3 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r2_bench_cfg3.log 2> gpurun_out/r2_bench_cfg3.err
-tail -3 gpurun_out/r2_pytest_all.log
+tail -3 gpurun_out/r2_pytest_all.log; tail -2 gpurun_out/r2_pytest_ctx_staged.log; cut -c1-200 gpurun_out/r2_attention_ctx_staged.jsonl
 cat gpurun_out/r2_prefix_math_micro.jsonl | cut -c1-260
 cut -c1-200 gpurun_out/r2_bench_default.log gpurun_out/r2_bench_poly.log gpurun_out/r2_bench_ragged_h2d.log gpurun_out/r2_bench_cfg4.log gpurun_out/r2_bench_cfg3.log
