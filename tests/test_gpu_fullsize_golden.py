@@ -1,0 +1,44 @@
+"""Full-size parity: the bench's own models (19 M-parameter VGG+BLSTM CTC-attention model, 4x1024 RNNLM, unscaled
+random-init output layers) at the bench's decode settings against N-best lists the UNMODIFIED reference produced in
+the build container (tests/golden/beam_nbest_fullsize.npz, tools/make_golden.py fullsize).  The other end-to-end
+tests use small models with sharpened output layers; this one has the bench's near-tied scores (runner-up gaps of
+1e-5 .. 7e-4 in mean score), so a different 1-best is accepted when it is a tie by the reference's own scores
+(test_gpu_decode._compare)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+# Written without a GPU at hand (round 1 ran out of GPU minutes): until a run on the B200 has confirmed it this
+# test only runs on request, so that the suite the driver runs stays exactly the one that was last seen green.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("E2E_UNVALIDATED_TESTS") != "1", reason="not yet confirmed on a B200 (set E2E_UNVALIDATED_TESTS=1)")]
+
+
+def test_fullsize_models_match_the_reference_nbest(cuda, tmp_path):
+    import yaml
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth
+    from tests.test_gpu_decode import _compare
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "beam_nbest_fullsize.npz"), allow_pickle=False)
+    beam, lm_w, ctc_w = int(gold["beam"]), float(gold["lm_w"]), float(gold["ctc_w"])
+    asr, lm = synth.build_asr(31, seed=0), synth.build_lm(31, seed=1)
+    lm_path, lm_cfg = str(tmp_path / "lm.pth"), str(tmp_path / "lm.yaml")
+    torch.save({"model": lm.state_dict()}, lm_path)
+    yaml.safe_dump({"model": synth.LM_MODEL_CFG}, open(lm_cfg, "w"))
+    dec = BeamDecoder(asr, None, beam, 0.01, 0.2, lm_path=lm_path, lm_config=lm_cfg, lm_weight=lm_w, ctc_weight=ctc_w).to(cuda)
+    cases = range(int(gold["n_cases"]))
+    utts = [int(gold["case%d_utt" % c]) for c in cases]
+    lens = [int(gold["case%d_len" % c]) for c in cases]
+    order = sorted(cases, key=lambda c: -lens[c])
+    feat, fl = synth.padded_batch([utts[c] for c in order], [lens[c] for c in order])
+    out = dec.decode_batch(feat.to(cuda), fl.to(cuda))                       # all fixtures in one batch, as the bench decodes
+    same = ties = 0
+    for k, c in enumerate(order):
+        ref = [(gold["case%d_tok%d" % (c, j)], gold["case%d_sc%d" % (c, j)], gold["case%d_avg%d" % (c, j)])
+               for j in range(int(gold["case%d_nbest" % c]))]
+        assert len(out[k]) == len(ref)
+        s, t = _compare(out[k], ref, "full-size case %d (%d frames)" % (c, lens[c]))
+        same, ties = same + s, ties + t
+    print("full-size models: identical 1-best %d/%d, score ties %d" % (same, len(order), ties))
+    assert same >= 3                                                        # the three fixtures whose runner-up gap is >= 2e-4

@@ -9,6 +9,10 @@
   ``BeamDecoder`` (src/decode.py) driving the reference ``ASR``/``RNNLM`` loaded with the weights
   of ``e2e_asr_pytorch_b200.synth``'s tiny random-init models, on seeded synthetic utterances.
 
+* ``beam_nbest_fullsize.npz`` — the same for the FULL-SIZE bench models (synth.ASR_MODEL_CFG: librispeech_asr.yaml dims
+  with the VGG front end, 19 M parameters; 4x1024 RNNLM; output layers unscaled, exactly what bench.py builds) at the
+  bench's decode settings (beam 8, ctc 0.5, lm 0.5, ratios 0.01 / 0.2) on a few short utterances.
+
 The reference cannot travel to the GPU box, these vectors can.
 """
 import copy
@@ -102,9 +106,44 @@ def beam_nbest(ref):
     print("beam_nbest_tiny.npz: %d cases" % n_case)
 
 
+FULLSIZE_CASES = [(900001, 152), (900002, 240), (900003, 320), (900004, 480), (900005, 640)]      # (utterance id, input frames)
+
+
+def beam_nbest_fullsize(ref):
+    vocab, beam, lm_w, ctc_w = 31, 8, 0.5, 0.5
+    mine = synth.build_asr(vocab, seed=0)
+    rasr = ref.ASR(synth.FEAT_DIM, vocab, True, **copy.deepcopy(synth.ASR_MODEL_CFG)).eval()
+    rasr.load_state_dict(mine.state_dict())
+    lm = synth.build_lm(vocab, seed=1)
+    tmp = tempfile.mkdtemp()
+    torch.save({"model": lm.state_dict()}, os.path.join(tmp, "lm.pth"))
+    yaml.safe_dump({"model": synth.LM_MODEL_CFG}, open(os.path.join(tmp, "lm.yaml"), "w"))
+    dec = ref.BeamDecoder(rasr, None, beam, 0.01, 0.2, lm_path=os.path.join(tmp, "lm.pth"),
+                          lm_config=os.path.join(tmp, "lm.yaml"), lm_weight=lm_w, ctc_weight=ctc_w)
+    out = {"beam": np.int32(beam), "lm_w": np.float32(lm_w), "ctc_w": np.float32(ctc_w), "n_cases": np.int32(len(FULLSIZE_CASES))}
+    for k, (utt, n) in enumerate(FULLSIZE_CASES):
+        with torch.no_grad():
+            hyps = dec(synth.utterance(utt, n)[None], torch.LongTensor([n]))
+        key = "case%d" % k
+        out[key + "_utt"], out[key + "_len"], out[key + "_nbest"] = np.int32(utt), np.int32(n), np.int32(len(hyps))
+        for j, h in enumerate(hyps):
+            out["%s_tok%d" % (key, j)] = np.array(h.outIndex, np.int32)
+            out["%s_sc%d" % (key, j)] = np.array([float(s) for s in h.output_scores], np.float32)
+            out["%s_avg%d" % (key, j)] = np.float32(float(h.avgScore()))
+        print("  full-size case %d: %d frames, %d tokens, best mean score %.6f, runner-up gap %.3g"
+              % (k, n, len(hyps[0].outIndex), float(hyps[0].avgScore()), float(hyps[0].avgScore()) - float(hyps[1].avgScore())), flush=True)
+    np.savez_compressed(os.path.join(OUT, "beam_nbest_fullsize.npz"), **out)
+    print("beam_nbest_fullsize.npz: %d cases" % len(FULLSIZE_CASES))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref = refload.load()
     torch.set_num_threads(4)
-    prefix_chains(ref)
-    beam_nbest(ref)
+    if len(sys.argv) > 1 and sys.argv[1] == "fullsize":      # leaves the other fixtures untouched
+        torch.set_num_threads(8)
+        beam_nbest_fullsize(ref)
+    else:
+        prefix_chains(ref)
+        beam_nbest(ref)
+        beam_nbest_fullsize(ref)
