@@ -164,6 +164,7 @@ def run_b200(args):
     batches = shard.make_batches(shards[rank], lengths, args.max_utts, args.max_padded_frames)
     cap = int(np.ceil(lengths.max() * MAX_RATIO)) + 1
     rows = max(len(s) for s in shards)
+    rsize = shard.ragged_size(shards, lengths, BEAM, MAX_RATIO) if args.ragged_gather else 0
 
     host = [make_features(b, lengths, pin=True) for b in batches]            # pinned host buffers
     resident = [(f.to(dev), l.to(dev)) for f, l in host]                      # HBM-resident copies
@@ -189,7 +190,10 @@ def run_b200(args):
         pad = lambda a: torch.nn.functional.pad(a, (0, width - a.shape[2]))
         tok = torch.cat([pad(p[0]) for p in parts]); sc = torch.cat([pad(p[1]) for p in parts])
         ln = torch.cat([p[2] for p in parts]); avg = torch.cat([p[3] for p in parts]); n = torch.cat([p[4] for p in parts])
-        local_buf = shard.pack_nbest(ids, tok, sc, ln, avg, n, cap, rows)
+        if args.ragged_gather:                                                # 4.5x fewer bytes through the gather (shard.py)
+            local_buf = shard.pack_nbest_ragged(ids, tok, sc, ln, avg, n, shards[rank], lengths, BEAM, MAX_RATIO, rsize)
+        else:
+            local_buf = shard.pack_nbest(ids, tok, sc, ln, avg, n, cap, rows)
         full = shard.gather_nbest(local_buf, dev)                             # the one collective (no-op at N=1)
         return local_buf, full
 
@@ -243,7 +247,14 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
         return
-    ok = int((full[:, 0] >= 0).sum()) == n_total
+    if args.ragged_gather:
+        try:
+            shard.unpack_nbest_ragged(full, shards, lengths, BEAM, MAX_RATIO, rsize)
+            ok = True
+        except AssertionError:
+            ok = False
+    else:
+        ok = int((full[:, 0] >= 0).sum()) == n_total
     line = {
         "metric": METRIC, "value": n_total * args.steps / (ms * 1e-3), "unit": "utts/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -255,7 +266,7 @@ def run_b200(args):
                    "h2d": "valid frames only, one copy per utterance" if args.ragged_h2d else "padded [U,Lmax,D] tensor, one copy",
                    "lm_gemm_operands": dec.lm_split, "vgg_gemm_operands": dec.vgg_split,
                    "l2": "inputs (%.1f GB features + GB-scale prefix states per batch) exceed the 126 MB L2; no flush needed" % (in_bytes / 1e9),
-                   "parallelism": "utterance shards x%d, one all-gather of N-best" % world},
+                   "parallelism": "utterance shards x%d, one all-gather of N-best%s" % (world, " (ragged buffer)" if args.ragged_gather else "")},
         "e2e": {"value": n_total * args.steps / (e2e_ms * 1e-3), "unit": "utts/s",
                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(local_buf.numel() * 4)},
         "gpu_launches": int(launches),
@@ -389,6 +400,7 @@ def main():
                     help="log-add-exp evaluator of the prefix-score kernel (default: the decoder's, lut)")
     ap.add_argument("--ragged-h2d", action="store_true",
                     help="e2e leg: copy only the valid frames of every utterance (BeamDecoder.decode_batch_from_host)")
+    ap.add_argument("--ragged-gather", action="store_true", help="gather the ragged N-best buffer (shard.pack_nbest_ragged)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0)

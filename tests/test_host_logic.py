@@ -233,3 +233,39 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert "median" not in d["cpu_baseline"]["sample"]                      # 40 frames is not the workload's median
     quiet = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert quiet.returncode == 0 and quiet.stdout.strip() == ""
+
+
+def test_ragged_nbest_buffer_layout_and_size():
+    """shard.pack_nbest_ragged / unpack_nbest_ragged: round trip in any decode order, lost utterances and over-long
+    hypotheses are detected, and for the bench workload the buffer is > 4x smaller than the rectangular one."""
+    from e2e_asr_pytorch_b200 import shard, synth
+    lengths = np.array([40, 80, 64, 120, 44, 200, 52])
+    beam, ratio = 3, 0.2
+    shards = shard.plan_shards(lengths, 2, ratio)
+    size = shard.ragged_size(shards, lengths, beam, ratio)
+    bufs = []
+    for ids in shards:
+        order = list(ids[::-1])                                   # decode order != layout order
+        out = _fake_decode(lengths, beam, ratio)(order)
+        bufs.append(shard.pack_nbest_ragged(order, *out, ids, lengths, beam, ratio, size))
+        assert bufs[-1].shape == (size,)
+    tok, sc, ln, avg, n = shard.unpack_nbest_ragged(torch.cat(bufs), shards, lengths, beam, ratio, size)
+    want = _fake_decode(lengths, beam, ratio)(list(range(len(lengths))))
+    for a, b in zip((tok, sc, ln, avg, n), want):
+        assert torch.equal(a, b)
+    # a shard that did not decode one of its utterances is noticed
+    ids = shards[0]
+    part = _fake_decode(lengths, beam, ratio)(list(ids[1:]))
+    holed = shard.pack_nbest_ragged(list(ids[1:]), *part, ids, lengths, beam, ratio, size)
+    with pytest.raises(AssertionError):
+        shard.unpack_nbest_ragged(torch.cat([holed, bufs[1]]), shards, lengths, beam, ratio, size)
+    # a hypothesis longer than the layout allows is an error, not a truncation
+    bad = list(_fake_decode(lengths, beam, ratio)([int(ids[0])]))
+    bad[0] = torch.nn.functional.pad(bad[0], (0, 8)); bad[1] = torch.nn.functional.pad(bad[1], (0, 8)); bad[2] = bad[2] + 5
+    with pytest.raises(ValueError):
+        shard.pack_nbest_ragged([int(ids[0])], *bad, ids, lengths, beam, ratio, size)
+    # the bench workload: ragged vs rectangular bytes per rank
+    big = synth.devclean_lengths(2620, seed=2)
+    one = shard.plan_shards(big, 1, 0.2)
+    cap = int(np.ceil(big.max() * 0.2)) + 1
+    assert shard.ragged_size(one, big, 8, 0.2) * 4.0 < 2620 * shard.row_width(8, cap) * 4 / 4.0

@@ -24,7 +24,7 @@ E2E_AF_CTX_STAGED=1 timeout 90 python bench.py --steps 2 --warmup 3 --no-cpu-bas
 # 3. the decode with the polynomial evaluator (roofline.frac in-decode) next to the default
 timeout 90 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_default.log 2> gpurun_out/r2_bench_default.err
 timeout 90 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --prefix-math poly > gpurun_out/r2_bench_poly.log 2> gpurun_out/r2_bench_poly.err
-timeout 90 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --ragged-h2d > gpurun_out/r2_bench_ragged_h2d.log 2> gpurun_out/r2_bench_ragged_h2d.err
+timeout 90 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --ragged-h2d --ragged-gather > gpurun_out/r2_bench_ragged_h2d.log 2> gpurun_out/r2_bench_ragged_h2d.err
 # 4. the two BASELINE configurations the bench does not run (one pass each; cfg3 in memory-budgeted batches)
 timeout 150 python tools/bench_config.py --cfg 4 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r2_bench_cfg4.log 2> gpurun_out/r2_bench_cfg4.err
 timeout 240 python tools/bench_config.py --cfg 3 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r2_bench_cfg3.log 2> gpurun_out/r2_bench_cfg3.err
