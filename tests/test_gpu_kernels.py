@@ -186,6 +186,21 @@ def test_prefix_score_machine_filling_launch(cuda, vocab, beam, n_cand, flags):
     print("machine-filling launch V=%d B=%d: max |gpu-oracle| = %.3g" % (vocab, beam, w))
 
 
+@pytest.mark.parametrize("beam,n_cand,flags", [(8, 12, 0), (8, 12, "skip"), (4, 6, "skip")])
+def test_prefix_score_bench_sized_launch(cuda, beam, n_cand, flags):
+    """>= 1000 CTAs in one launch: the grid size from which the 16-frame-tile instantiations are taken
+    (prefix_score.cu: E2E_PREFIX_SMALL_TILE_FROM) — the fixed-shape <32,96,tensor-map,16> kernel that the bench's
+    machine-filling launches run (beam 8) and the generic 16-frame-tile kernel (beam 4)."""
+    _, L = _ops()
+    rng = np.random.default_rng(23)
+    n_utts = 1100 if beam == 8 else 1300
+    t_lens = [int(t) for t in rng.integers(5, 48, n_utts)]
+    t_lens[0], t_lens[1], t_lens[2] = 83, 5, 16
+    fl = L.PREFIX_SKIP_DEAD_ROWS if flags == "skip" else 0
+    w = _chain(cuda, rng, n_utts=n_utts, t_lens=t_lens, vocab=31, beam=beam, n_cand=n_cand, n_steps=4, flags=fl)
+    print("bench-sized launch (%d CTAs) B=%d: max |gpu-oracle| = %.3g" % (n_utts, beam, w))
+
+
 def test_prefix_score_midsize_vocab_rows(cuda):
     rng = np.random.default_rng(16)
     _chain(cuda, rng, n_utts=2, t_lens=[50, 41], vocab=200, beam=3, n_cand=4, n_steps=5)
