@@ -291,92 +291,133 @@ def run_b200(args):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference, one utterance per worker process (the reference fans
-# utterances out to joblib processes, bin/test_asr.py:138-139)
+# CPU arm: the UNMODIFIED reference (oracle/_ref: its decode path byte-compiled by oracle/ref_stage.py; imported from
+# /root/reference where that exists), driven the way bin/test_asr.py drives it — a deep copy of the BeamDecoder inside
+# functools.partial(beam_decode, ...), utterances fanned out with joblib.Parallel (bin/test_asr.py:108-109,138-139).
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker(job):
-    uid, n = job
-    import torch as th
-    th.set_num_threads(1)
-    from oracle import beam_oracle as BO
-    from e2e_asr_pytorch_b200 import synth
-    global _CPU_MODELS
+def cpu_model_name():
     try:
-        asr, lm = _CPU_MODELS
-    except NameError:
-        asr, lm = synth.build_asr(VOCAB, seed=0), synth.build_lm(VOCAB, seed=1)
-        _CPU_MODELS = (asr, lm)
-    feat = synth.utterance(uid, n)[None]
-    t0 = time.time()
-    with th.no_grad():
-        nb = BO.decode_utterance(asr, feat, th.LongTensor([n]), BEAM, MIN_RATIO, MAX_RATIO, lm=lm,
-                                 lm_weight=LM_W, ctc_weight=CTC_W, trace=None)
-    steps = int(np.ceil(n * MAX_RATIO))
-    frames = n // 4
-    return time.time() - t0, (1 + (steps - 1) * BEAM) * int(1.5 * BEAM) * frames, len(nb)
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 
 
-def cpu_sample_jobs(n_jobs, frames=640):
-    """Bounded sample: ``n_jobs`` utterances of ``frames`` input frames each.  The default is the
-    workload's MEDIAN length (6.4 s); one such utterance costs ~25 s of one core, and the cost grows
-    ~quadratically with the length (decode steps x encoder frames), so against the workload's mean
-    cost (equivalent to ~840 frames) utts/s on this sample still flatters the CPU by ~1.7x."""
-    return [(100000 + k, frames) for k in range(n_jobs)]
+def stratified_sample(lengths, n):
+    """Utterance ids at the quantile midpoints (k + 0.5) / n of the sorted lengths of the set."""
+    order = np.argsort(np.asarray(lengths), kind="stable")
+    pos = np.minimum(((np.arange(n) + 0.5) / n * len(order)).astype(np.int64), len(order) - 1)
+    return [int(order[p]) for p in pos]
 
 
-def cpu_pass(pool, jobs):
-    t0 = time.time()
-    res = pool.map(_cpu_worker, jobs)
-    wall = time.time() - t0
-    return wall, sum(r[1] for r in res)
+def cand_frames(n_frames):
+    steps = int(np.ceil(n_frames * MAX_RATIO))
+    return (1 + (steps - 1) * BEAM) * int(1.5 * BEAM) * (n_frames // 4) if steps > 0 else 0
+
+
+class ReferenceCpu:
+    """The reference's BeamDecoder on the host, with the bench's weights and decode settings."""
+
+    def __init__(self):
+        import copy
+        import tempfile
+        import yaml
+        from functools import partial
+        from oracle import refload
+        from e2e_asr_pytorch_b200 import synth
+        self.refload = refload
+        ref = refload.load()
+        self.kind = ref.kind
+        test_asr = refload.load_test_asr()
+        rasr = ref.ASR(synth.FEAT_DIM, VOCAB, True, **copy.deepcopy(synth.ASR_MODEL_CFG)).eval()
+        rasr.load_state_dict(synth.build_asr(VOCAB, seed=0).state_dict())          # same weights as the B200 arm
+        tmp = tempfile.mkdtemp(prefix="e2e_ref_")
+        torch.save({"model": synth.build_lm(VOCAB, seed=1).state_dict()}, os.path.join(tmp, "lm.pth"))
+        yaml.safe_dump({"model": synth.LM_MODEL_CFG}, open(os.path.join(tmp, "lm.yaml"), "w"))
+        dec = ref.BeamDecoder(rasr, None, BEAM, MIN_RATIO, MAX_RATIO, lm_path=os.path.join(tmp, "lm.pth"),
+                              lm_config=os.path.join(tmp, "lm.yaml"), lm_weight=LM_W, ctc_weight=CTC_W)
+        self.func = partial(test_asr.beam_decode, model=copy.deepcopy(dec), device="cpu")   # bin/test_asr.py:108-109
+
+    @staticmethod
+    def data(uid, n):
+        from e2e_asr_pytorch_b200 import synth
+        return (["utt%d" % uid], synth.utterance(uid, n)[None], torch.LongTensor([n]), torch.zeros(1, 1, dtype=torch.long))
+
+    def run(self, jobs, n_jobs, threads):
+        """jobs: [(utterance id, frames)], decoded longest first.  ``threads``: torch intra-op threads per worker
+        (None = the library default, as shipped).  Returns (wall seconds, results)."""
+        from joblib import Parallel, delayed
+        jobs = sorted(jobs, key=lambda j: -j[1])
+        t0 = time.time()
+        res = Parallel(n_jobs=n_jobs, initializer=self.refload.worker_init, initargs=(None, threads))(
+            delayed(self.func)(self.data(u, n)) for u, n in jobs)
+        return time.time() - t0, res
 
 
 def cpu_baseline(args, sample_utts=None):
-    import multiprocessing as mp
+    """Bounded CPU figure printed beside the B200 line: one median-length utterance per core."""
     cores = len(os.sched_getaffinity(0))
     procs = max(1, min(cores, args.cpu_procs or cores))
     n_jobs = sample_utts or procs
-    jobs = cpu_sample_jobs(n_jobs, args.cpu_frames)
-    ctx = mp.get_context("fork")
-    with ctx.Pool(procs) as pool:
-        wall, units = cpu_pass(pool, jobs)
-    return {"value": n_jobs / wall, "unit": "utts/s", "cores": procs, "kind": "port",
-            "sample": "%d synthetic utts of %d input frames (%.1f s audio%s) each, one per process, "
-                      "oracle/beam_oracle.py (numpy prefix score + PyTorch-CPU modules), %.1f s wall"
-                      % (n_jobs, args.cpu_frames, args.cpu_frames / 100.0, MEDIAN_NOTE if args.cpu_frames == 640 else "", wall),
-            "cand_frames_per_s": units / wall}
+    ref = ReferenceCpu()
+    jobs = [(100000 + k, args.cpu_frames) for k in range(n_jobs)]
+    ref.run([(200000 + k, 80) for k in range(procs)], procs, 1)                   # spawns the workers, imports, first touch
+    wall, _ = ref.run(jobs, procs, 1)
+    return {"value": n_jobs / wall, "unit": "utts/s", "cores": procs, "kind": "reference", "cpu": cpu_model_name(),
+            "sample": "%d synthetic utts of %d input frames (%.1f s audio%s) each; the unmodified reference BeamDecoder (%s) through "
+                      "bin/test_asr.py::beam_decode and joblib.Parallel(n_jobs=%d), 1 torch thread per worker, %.1f s wall; the CPU cost "
+                      "grows ~L^2, so the median length flatters the CPU by ~1.8x against the workload's mean cost — "
+                      "`bench.py --impl reference` decodes a length-stratified sample of the set itself"
+                      % (n_jobs, args.cpu_frames, args.cpu_frames / 100.0, MEDIAN_NOTE if args.cpu_frames == 640 else "",
+                         "oracle/_ref" if ref.kind == "staged" else "/root/reference", procs, wall),
+            "cand_frames_per_s": sum(cand_frames(n) for _, n in jobs) / wall}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
     procs = max(1, min(cores, args.cpu_procs or cores))
-    jobs = cpu_sample_jobs(args.cpu_sample or procs, args.cpu_frames)
-    ctx = mp.get_context("fork")
-    with ctx.Pool(procs) as pool:
-        for _ in range(args.warmup):          # builds the models in every worker; short utterances keep it cheap
-            cpu_pass(pool, cpu_sample_jobs(procs, 80))
-        t0 = time.time()
-        units = 0
-        for _ in range(args.steps):
-            w, u = cpu_pass(pool, jobs)
-            units += u
-        wall = time.time() - t0
-    value = len(jobs) * args.steps / wall
-    sample = "%d synthetic utts of %d input frames (%sCPU cost grows ~L^2, the workload's " \
-             "mean-cost-equivalent length is ~840 frames) per step, one per process, oracle port of the reference " \
-             "(the reference is Python under /root/reference and cannot travel to the GPU box)" \
-             % (len(jobs), args.cpu_frames, "the workload's median length; " if args.cpu_frames == 640 else "")
+    lengths = workload_lengths(1, N_UTTS)                                         # the cfg2 set of one GPU
+    per_step = max(1, (args.cpu_sample or 64) // max(1, args.steps))
+    ids = stratified_sample(lengths, per_step * args.steps)
+    jobs = [(i, int(lengths[i])) for i in ids]
+    ref = ReferenceCpu()
+    for _ in range(max(1, args.warmup)):                                          # workers up, modules imported, caches warm
+        ref.run([(200000 + k, 80) for k in range(procs)], procs, 1)
+    # best effort: one worker per core, one torch thread each; the K steps' samples are ONE joblib.Parallel region
+    # (the reference iterates a whole data set the same way), so no core idles at a step boundary
+    wall, res = ref.run(jobs, procs, 1)
+    assert len(res) == len(jobs) and all(len(r[1]) > 0 for r in res)
+    value = len(jobs) / wall
+    units = sum(cand_frames(n) for _, n in jobs)
+    lens = sorted(n for _, n in jobs)
+    sample = "%d utterances of the cfg2 set at the quantile midpoints of its length distribution (%d..%d input frames, mean %d; "              "same ids, features and weights as the B200 arm), %d per step, decoded by the unmodified reference (%s: "              "src/decode.py BeamDecoder + src/ctc.py CTCPrefixScore) through bin/test_asr.py::beam_decode and "              "joblib.Parallel(n_jobs=%d), 1 torch thread per worker, longest first"              % (len(jobs), lens[0], lens[-1], int(np.mean(lens)), per_step, "oracle/_ref" if ref.kind == "staged" else "/root/reference", procs)
+    shipped = None
+    if not args.no_as_shipped:
+        # as shipped (script/test.sh:15): --njobs 4, torch threads left at the library default; on a smaller stratified sample
+        sub = stratified_sample(lengths, args.as_shipped_sample)
+        sjobs = [(i, int(lengths[i])) for i in sub]
+        env_threads = os.environ.pop("OMP_NUM_THREADS", None)                     # torchrun exports OMP_NUM_THREADS=1
+        try:
+            swall, sres = ref.run(sjobs, 4, None)
+        finally:
+            if env_threads is not None:
+                os.environ["OMP_NUM_THREADS"] = env_threads
+        shipped = {"value": len(sjobs) / swall, "unit": "utts/s", "n_jobs": 4, "torch_threads": "library default",
+                   "sample": "%d utterances at the quantile midpoints of the same set (%d..%d frames), %.1f s wall"
+                             % (len(sjobs), min(n for _, n in sjobs), max(n for _, n in sjobs), swall)}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "utts/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2 model/decoder settings on a bounded sample: " + sample},
-        "cpu_baseline": {"value": value, "unit": "utts/s", "cores": procs, "kind": "port", "sample": sample,
-                         "cand_frames_per_s": units / wall},
+        "config": {"workload": "cfg2: char V=31 VGG+BLSTM CTC-attention (librispeech_asr.yaml dims, vgg=1) + 4x1024 RNNLM, "
+                               "beam 8, ctc 0.5, lm 0.5, max_len_ratio 0.2, dev-clean-like lengths, random init; bounded sample: " + sample},
+        "cpu_baseline": {"value": value, "unit": "utts/s", "cores": procs, "kind": "reference", "cpu": cpu_model_name(),
+                         "sample": sample, "cand_frames_per_s": units / wall, "wall_s": wall, "as_shipped": shipped},
         "e2e": {"value": value, "unit": "utts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
@@ -405,6 +446,8 @@ def main():
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--cpu-frames", type=int, default=640, help="length of the CPU sample's utterances (640 = workload median)")
+    ap.add_argument("--no-as-shipped", action="store_true", help="reference arm: skip the as-shipped (--njobs 4) measurement")
+    ap.add_argument("--as-shipped-sample", type=int, default=8, help="reference arm: utterances of the as-shipped measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

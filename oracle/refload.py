@@ -1,30 +1,41 @@
-"""Import the UNMODIFIED reference from /root/reference (TEST INFRASTRUCTURE).
+"""Import the UNMODIFIED reference (TEST / BASELINE INFRASTRUCTURE).
 
-Only usable in the build container: ``/root/reference`` does not exist on the
-GPU box, so nothing that runs there may call :func:`load`.  It is used by
-``tools/make_golden.py`` (fixture generation) and by the ``not gpu`` tests that
-pin the restatements in ``oracle/`` against the live reference.
+Two places it can come from:
 
-``src/util.py:7-9`` imports matplotlib at module top; matplotlib is absent in
-this image, so a stub module is installed first.
+* ``/root/reference`` — the live source tree, present only in the build container.  Used by
+  ``tools/make_golden.py`` (fixture generation) and by the ``not gpu`` tests that pin the restatements
+  in ``oracle/`` against the reference.
+* ``oracle/_ref/`` — the same files byte-compiled by ``oracle/ref_stage.py`` (sourceless ``.pyc``,
+  git-ignored, shipped to the GPU box).  Used there by ``bench.py --impl reference``, ``bench.py``'s
+  ``cpu_baseline`` leg and the drop-in test.  TorchScript needs source text, so the two
+  ``torch.jit.ScriptModule`` classes of ``src/module.py`` (liGRU, not on the decode path) are defined with
+  scripting switched off for the duration of the import; nothing else differs.
+
+``src/util.py:7-9`` imports matplotlib at module top; matplotlib is absent in this image, so a stub
+module is installed first.  ``bin/test_asr.py`` imports ``src.solver``
+(tensorboard) and ``src.data`` (librosa): stubs stand in for them while it is imported — only its
+module-level ``beam_decode`` function (``bin/test_asr.py:159-173``) is used.
 """
 import os
 import sys
 import types
 
+from . import ref_stage
+
 REFERENCE_ROOT = os.environ.get("E2E_REFERENCE_ROOT", "/root/reference")
+_loaded = None       # (kind, root)
 
 
 def available():
+    """The live source tree is present (build container only)."""
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "src", "ctc.py"))
 
 
-def load():
-    """Returns a namespace with the reference's ASR, RNNLM, BeamDecoder,
-    Hypothesis, CTCPrefixScore classes and the repo root."""
-    if not available():
-        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
-    sys.dont_write_bytecode = True      # the reference tree is read-only
+def staged_available():
+    return ref_stage.staged()
+
+
+def _stub_matplotlib():
     if "matplotlib" not in sys.modules:
         mpl = types.ModuleType("matplotlib")
         mpl.use = lambda *a, **k: None
@@ -32,13 +43,91 @@ def load():
         mpl.pyplot = plt
         sys.modules["matplotlib"] = mpl
         sys.modules["matplotlib.pyplot"] = plt
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
-    from src.asr import ASR
-    from src.lm import RNNLM
-    from src.decode import BeamDecoder, Hypothesis
-    from src.ctc import CTCPrefixScore
-    ns = types.SimpleNamespace(ASR=ASR, RNNLM=RNNLM, BeamDecoder=BeamDecoder,
-                               Hypothesis=Hypothesis, CTCPrefixScore=CTCPrefixScore,
-                               root=REFERENCE_ROOT)
-    return ns
+
+
+class _NoScript:
+    """torch.jit scripting off while sourceless modules are imported (TorchScript wants source text)."""
+
+    def __enter__(self):
+        import torch.jit._state as st
+        self.st, self.prev = st, st._enabled.enabled
+        st._enabled.enabled = False
+
+    def __exit__(self, *exc):
+        self.st._enabled.enabled = self.prev
+
+
+def _root(staged):
+    global _loaded
+    if staged is None:
+        staged = not available()
+    kind = "staged" if staged else "live"
+    if _loaded is not None:
+        if _loaded[0] != kind:
+            raise RuntimeError("the reference is already imported from the %s tree in this process" % _loaded[0])
+        return _loaded
+    if staged:
+        if not staged_available():
+            raise RuntimeError("oracle/_ref is not built: run __graft_entry__.build() where /root/reference exists")
+        root = ref_stage.OUT
+    else:
+        if not available():
+            raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+        root = REFERENCE_ROOT
+        sys.dont_write_bytecode = True      # the reference tree is read-only
+    _stub_matplotlib()
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    _loaded = (kind, root)
+    return _loaded
+
+
+def load(staged=None):
+    """Namespace with the reference's ASR, RNNLM, BeamDecoder, Hypothesis, CTCPrefixScore classes.
+    ``staged=None``: the live tree if present, else ``oracle/_ref``; True / False force one of them."""
+    kind, root = _root(staged)
+    with _NoScript() if kind == "staged" else _Null():
+        from src.asr import ASR
+        from src.lm import RNNLM
+        from src.decode import BeamDecoder, Hypothesis
+        from src.ctc import CTCPrefixScore
+    return types.SimpleNamespace(ASR=ASR, RNNLM=RNNLM, BeamDecoder=BeamDecoder, Hypothesis=Hypothesis,
+                                 CTCPrefixScore=CTCPrefixScore, root=root, kind=kind)
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def load_test_asr(staged=None):
+    """The reference's ``bin.test_asr`` module (for ``beam_decode``, bin/test_asr.py:159-173)."""
+    kind, root = _root(staged)
+    load(staged)
+    added = []
+    for name, attrs in (("src.solver", {"BaseSolver": object}), ("src.data", {"load_dataset": None, "load_wav_dataset": None})):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+            added.append(name)
+    try:
+        with _NoScript() if kind == "staged" else _Null():
+            import bin.test_asr as mod
+    finally:
+        for name in added:
+            sys.modules.pop(name, None)
+    return mod
+
+
+def worker_init(staged=None, threads=None):
+    """Initialiser of a joblib/loky worker process: the same import environment as the parent (path, matplotlib /
+    solver / data stand-ins), so that a pickled ``partial(beam_decode, model=decoder)`` can be rebuilt there.
+    ``threads``: torch intra-op threads of the worker (None = the library default)."""
+    load_test_asr(staged)
+    if threads is not None:
+        import torch
+        torch.set_num_threads(int(threads))

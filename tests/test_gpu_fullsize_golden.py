@@ -10,10 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-# Written without a GPU at hand (round 1 ran out of GPU minutes): until a run on the B200 has confirmed it this
-# test only runs on request, so that the suite the driver runs stays exactly the one that was last seen green.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("E2E_UNVALIDATED_TESTS") != "1", reason="not yet confirmed on a B200 (set E2E_UNVALIDATED_TESTS=1)")]
+pytestmark = pytest.mark.gpu      # confirmed on a B200 (profiles/r02_a_pytest_gpu.txt)
 
 
 def test_fullsize_models_match_the_reference_nbest(cuda, tmp_path):

@@ -3,15 +3,11 @@ csrc/common.cuh softplus_poly; 52 instead of 67.5 instructions per candidate-fra
 oracle, on the same beam-search-shaped chains and to the same tolerance as the default table math
 (test_gpu_kernels.py: 1e-4 absolute or 2 ulp).  tools/emulate_prefix_math.py predicts <= 1 ulp.
 """
-import os
 
 import numpy as np
 import pytest
 
-# Written without a GPU at hand (round 1 ran out of GPU minutes): until a run on the B200 has confirmed them these
-# tests only run on request, so that the suite the driver runs stays exactly the one that was last seen green.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("E2E_UNVALIDATED_TESTS") != "1", reason="not yet confirmed on a B200 (set E2E_UNVALIDATED_TESTS=1)")]
+pytestmark = pytest.mark.gpu      # confirmed on a B200 (profiles/r02_a_pytest_gpu.txt)
 
 
 def _flags(mode):
