@@ -362,7 +362,8 @@ def cpu_baseline(args, sample_utts=None):
     procs = max(1, min(cores, args.cpu_procs or cores))
     n_jobs = sample_utts or procs
     ref = ReferenceCpu()
-    jobs = [(100000 + k, args.cpu_frames) for k in range(n_jobs)]
+    frames = args.cpu_frames or 640
+    jobs = [(100000 + k, frames) for k in range(n_jobs)]
     ref.run([(200000 + k, 80) for k in range(procs)], procs, 1)                   # spawns the workers, imports, first touch
     wall, _ = ref.run(jobs, procs, 1)
     return {"value": n_jobs / wall, "unit": "utts/s", "cores": procs, "kind": "reference", "cpu": cpu_model_name(),
@@ -370,7 +371,7 @@ def cpu_baseline(args, sample_utts=None):
                       "bin/test_asr.py::beam_decode and joblib.Parallel(n_jobs=%d), 1 torch thread per worker, %.1f s wall; the CPU cost "
                       "grows ~L^2, so the median length flatters the CPU by ~1.8x against the workload's mean cost — "
                       "`bench.py --impl reference` decodes a length-stratified sample of the set itself"
-                      % (n_jobs, args.cpu_frames, args.cpu_frames / 100.0, MEDIAN_NOTE if args.cpu_frames == 640 else "",
+                      % (n_jobs, frames, frames / 100.0, MEDIAN_NOTE if frames == 640 else "",
                          "oracle/_ref" if ref.kind == "staged" else "/root/reference", procs, wall),
             "cand_frames_per_s": sum(cand_frames(n) for _, n in jobs) / wall}
 
@@ -383,8 +384,10 @@ def run_reference(args):
     procs = max(1, min(cores, args.cpu_procs or cores))
     lengths = workload_lengths(1, N_UTTS)                                         # the cfg2 set of one GPU
     per_step = max(1, (args.cpu_sample or 64) // max(1, args.steps))
-    ids = stratified_sample(lengths, per_step * args.steps)
-    jobs = [(i, int(lengths[i])) for i in ids]
+    if args.cpu_frames:                                                           # smoke runs: utterances of one given length
+        jobs = [(100000 + k, args.cpu_frames) for k in range(per_step * args.steps)]
+    else:
+        jobs = [(i, int(lengths[i])) for i in stratified_sample(lengths, per_step * args.steps)]
     ref = ReferenceCpu()
     for _ in range(max(1, args.warmup)):                                          # workers up, modules imported, caches warm
         ref.run([(200000 + k, 80) for k in range(procs)], procs, 1)
@@ -395,12 +398,20 @@ def run_reference(args):
     value = len(jobs) / wall
     units = sum(cand_frames(n) for _, n in jobs)
     lens = sorted(n for _, n in jobs)
-    sample = "%d utterances of the cfg2 set at the quantile midpoints of its length distribution (%d..%d input frames, mean %d; "              "same ids, features and weights as the B200 arm), %d per step, decoded by the unmodified reference (%s: "              "src/decode.py BeamDecoder + src/ctc.py CTCPrefixScore) through bin/test_asr.py::beam_decode and "              "joblib.Parallel(n_jobs=%d), 1 torch thread per worker, longest first"              % (len(jobs), lens[0], lens[-1], int(np.mean(lens)), per_step, "oracle/_ref" if ref.kind == "staged" else "/root/reference", procs)
+    what = "synthetic utterances of one fixed length" if args.cpu_frames else \
+        "utterances of the cfg2 set at the quantile midpoints of its length distribution"
+    sample = ("%d %s (%d..%d input frames, mean %d; same ids, features and weights as the B200 arm), %d per step, decoded by the "
+              "unmodified reference (%s: src/decode.py BeamDecoder + src/ctc.py CTCPrefixScore) through bin/test_asr.py::beam_decode "
+              "and joblib.Parallel(n_jobs=%d), 1 torch thread per worker, longest first"
+              % (len(jobs), what, lens[0], lens[-1], int(np.mean(lens)), per_step,
+                 "oracle/_ref" if ref.kind == "staged" else "/root/reference", procs))
     shipped = None
     if not args.no_as_shipped:
         # as shipped (script/test.sh:15): --njobs 4, torch threads left at the library default; on a smaller stratified sample
-        sub = stratified_sample(lengths, args.as_shipped_sample)
-        sjobs = [(i, int(lengths[i])) for i in sub]
+        if args.cpu_frames:
+            sjobs = [(300000 + k, args.cpu_frames) for k in range(args.as_shipped_sample)]
+        else:
+            sjobs = [(i, int(lengths[i])) for i in stratified_sample(lengths, args.as_shipped_sample)]
         env_threads = os.environ.pop("OMP_NUM_THREADS", None)                     # torchrun exports OMP_NUM_THREADS=1
         try:
             swall, sres = ref.run(sjobs, 4, None)
@@ -445,7 +456,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0)
-    ap.add_argument("--cpu-frames", type=int, default=640, help="length of the CPU sample's utterances (640 = workload median)")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="length of the CPU sample's utterances (default: 640 = the workload's median for the "
+                    "cpu_baseline leg; the reference arm decodes a length-stratified sample of the set unless a length is given)")
     ap.add_argument("--no-as-shipped", action="store_true", help="reference arm: skip the as-shipped (--njobs 4) measurement")
     ap.add_argument("--as-shipped-sample", type=int, default=8, help="reference arm: utterances of the as-shipped measurement")
     args = ap.parse_args()

@@ -38,6 +38,12 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "e2e_ctc_prefix_step_supported": (c_int, [c_int, c_int, c_int]),
+    "e2e_ctc_prefix_step": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                    c_void_p, c_int,
+                                    c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_int, c_int, c_int,
+                                    c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "e2e_beam_candidates": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "e2e_beam_combine_prune": (c_int, [c_void_p, c_int, c_void_p,
                                        c_void_p, c_int,
@@ -50,7 +56,7 @@ SIGNATURES = {
                                        c_void_p,
                                        c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                       c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+                                       c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "e2e_attention_loc_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
                                        c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "e2e_attention_loc_full": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

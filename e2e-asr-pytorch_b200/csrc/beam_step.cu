@@ -94,6 +94,7 @@ struct CombineParams {
     int *n_live, *n_active, *last_tok, *prefix_len; float *score_sum, *ctc_prob; int *prev_lane;
     int *parent_slot, *hist_tok, *hist_parent; float *hist_score;
     long long *parent_row, *last_tok64;     // optional 64-bit copies for the host's gathers (row = u*B + parent slot)
+    int *parent_tok;                        // optional: last token of each survivor's PARENT (-1: the empty prefix)
     int *fin_count, *fin_step, *fin_parent; float *fin_sum, *fin_score; int fin_cap;
     int *status;
 };
@@ -132,8 +133,12 @@ beam_combine_prune_kernel(const CombineParams p)
     float *w_delta = reinterpret_cast<float *>(w_cand + B * (C > 0 ? C : 1));
     float *top_v = w_delta + B * (C > 0 ? C : 1);              // [B][B] winners per parent
     int *top_i = reinterpret_cast<int *>(top_v + B * B);
+    int *par_tok = top_i + B * B;                              // [B] the parents' own last tokens
 
-    if (threadIdx.x < B) { cnt[threadIdx.x] = 0; term[threadIdx.x] = 0; }
+    if (threadIdx.x < B) {
+        cnt[threadIdx.x] = 0; term[threadIdx.x] = 0;
+        par_tok[threadIdx.x] = (p.step > 0 && threadIdx.x < live) ? p.last_tok[u * B + threadIdx.x] : -1;
+    }
     __syncthreads();
 
     if (w < live) {
@@ -276,6 +281,7 @@ beam_combine_prune_kernel(const CombineParams p)
             p.last_tok[o] = c_tok[i];
             if (p.last_tok64) p.last_tok64[o] = c_tok[i];
             if (p.parent_row) p.parent_row[o] = (long long)u * B + b;
+            if (p.parent_tok) p.parent_tok[o] = par_tok[b];
             p.prefix_len[o] = p.step + 1;
             p.score_sum[o] = c_sum[i];
             p.ctc_prob[o] = c_psi[i];
@@ -302,7 +308,7 @@ beam_combine_prune_kernel(const CombineParams p)
 static size_t combine_smem_bytes(int B, int C)
 {
     const int Cc = C > 0 ? C : 1;
-    return (size_t)(6 * B * B + 3 * B + 2 * B * Cc + 2 * B * B) * 4 + 16;
+    return (size_t)(6 * B * B + 4 * B + 2 * B * Cc + 2 * B * B) * 4 + 16;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -391,7 +397,7 @@ extern "C" int e2e_beam_combine_prune(const float *att_logits, int ld_att, const
                                       int *hist_tok, int *hist_parent, float *hist_score,
                                       int *fin_count, int *fin_step, int *fin_parent, float *fin_sum, float *fin_score,
                                       int fin_cap, int *status, int n_run,
-                                      long long *parent_row, long long *last_tok64, void *stream)
+                                      long long *parent_row, long long *last_tok64, int *parent_tok, void *stream)
 {
     using namespace e2e;
     const bool use_ctc = (flags & E2E_BEAM_USE_CTC) != 0, use_lm = (flags & E2E_BEAM_USE_LM) != 0;
@@ -412,7 +418,7 @@ extern "C" int e2e_beam_combine_prune(const float *att_logits, int ld_att, const
     p.flags = flags;
     p.n_live = n_live; p.n_active = n_active; p.last_tok = last_tok; p.prefix_len = prefix_len; p.score_sum = score_sum; p.ctc_prob = ctc_prob; p.prev_lane = prev_lane;
     p.parent_slot = parent_slot; p.hist_tok = hist_tok; p.hist_parent = hist_parent; p.hist_score = hist_score;
-    p.parent_row = parent_row; p.last_tok64 = last_tok64;
+    p.parent_row = parent_row; p.last_tok64 = last_tok64; p.parent_tok = parent_tok;
     p.fin_count = fin_count; p.fin_step = fin_step; p.fin_parent = fin_parent; p.fin_sum = fin_sum; p.fin_score = fin_score;
     p.fin_cap = fin_cap; p.status = status;
     const size_t smem = combine_smem_bytes(B, p.C);

@@ -360,6 +360,12 @@ static int make_posterior_map(CUtensorMap *map, const float *x, int Tmax, int U,
     return E2E_OK;
 }
 
+// the same tensor map for the fused per-step kernel (prefix_lazy.cu)
+int make_posterior_map_lazy(CUtensorMap *map, const float *x, int Tmax, int U, int Vp, int tile)
+{
+    return make_posterior_map(map, x, Tmax, U, Vp, tile);
+}
+
 }  // namespace e2e
 
 extern "C" int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int V, const int *enc_len,

@@ -127,6 +127,9 @@ class BeamDecoder(nn.Module):
         # polynomial: 23 % fewer instructions per candidate-frame, csrc/common.cuh; an experiment until measured on the GPU)
         self.prefix_math = os.environ.get("E2E_PREFIX_MATH", "lut")
         self.skip_dead_rows = True      # do not write state rows t < len(prefix) nobody reads back
+        # fused per-step prefix kernel with lazy state evaluation (csrc/prefix_lazy.cu): states only for the <= B
+        # hypotheses the beam kept, psi alone for the B*C candidates.  False: the eager kernel (csrc/prefix_score.cu)
+        self.lazy_prefix = os.environ.get("E2E_PREFIX_LAZY", "1") != "0"
         self.split_gemm = True          # fp32-accurate 3-way bf16 split of the recurrent GEMMs (stepper.py)
         # operand format of the RNNLM's recurrent GEMMs: "bf16x3" (six partial products) or "fp16x2" (three; every
         # input is a hidden state, |h| <= 1).  The environment variable is for A/B runs of the bench.
@@ -245,8 +248,9 @@ class BeamDecoder(nn.Module):
                 logits = F.linear(enc, lin.weight, lin.bias).contiguous()          # cuBLAS; ReLU + log-softmax fused in (1)
                 x = ops.ctc_log_softmax(logits, enc_len32, apply_relu=True)        # decode.py:94-95
                 del logits                                                         # [U,Tmax,V]: as large as x with a subword vocabulary
-                r_prev = ops.ctc_init_state(x, enc_len32)                          # decode.py:97
-                r_a = torch.empty((n_utts, t_max, beam * n_cand, 2), dtype=torch.float32, device=dev)
+                r_prev = r_init = ops.ctc_init_state(x, enc_len32)                 # decode.py:97
+                lazy = self.lazy_prefix and not self.fast_math and ops.prefix_step_supported(vocab, beam, n_cand)
+                r_a = torch.empty((n_utts, t_max, beam if lazy else beam * n_cand, 2), dtype=torch.float32, device=dev)
                 r_b = torch.empty_like(r_a)
             pflags = (L.PREFIX_FAST_MATH if self.fast_math else 0) | (L.PREFIX_SKIP_DEAD_ROWS if self.skip_dead_rows else 0)
             if not self.fast_math:
@@ -265,9 +269,16 @@ class BeamDecoder(nn.Module):
                     if self.profile_prefix:
                         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         ev0.record()
-                    ops.ctc_prefix_score(x, vocab, enc_len32, r_prev, buf.prev_lane.view(-1), buf.last_tok.view(-1),
-                                         buf.prefix_len.view(-1), buf.n_active, buf.cand, beam, n_cand, pflags,
-                                         psi=buf.psi, r_out=r_cur, status=buf.status, n_run=k)
+                    if lazy:
+                        # states of the live hypotheses from their parents' (the init buffer at steps 0 and 1) + psi of all candidates
+                        ops.ctc_prefix_step(x, vocab, enc_len32, r_init if step <= 1 else r_prev, buf.parent_slot.view(-1),
+                                            buf.last_tok.view(-1), buf.parent_tok.view(-1), buf.prefix_len.view(-1), buf.n_active,
+                                            buf.cand, beam, n_cand, pflags & ~L.PREFIX_SKIP_DEAD_ROWS,
+                                            psi=buf.psi, r_out=r_cur, status=buf.status, n_run=k)
+                    else:
+                        ops.ctc_prefix_score(x, vocab, enc_len32, r_prev, buf.prev_lane.view(-1), buf.last_tok.view(-1),
+                                             buf.prefix_len.view(-1), buf.n_active, buf.cand, beam, n_cand, pflags,
+                                             psi=buf.psi, r_out=r_cur, status=buf.status, n_run=k)
                     if self.profile_prefix:
                         ev1.record()
                         act = s_np > step                     # utterances that still decode at this step

@@ -86,6 +86,42 @@ def ctc_prefix_score(x, vocab, enc_len, r_prev, prev_lane, last_tok, prefix_len,
     return psi, r_out
 
 
+def prefix_step_supported(vocab, beam, n_cand):
+    return bool(L.load().e2e_ctc_prefix_step_supported(padded_vocab(vocab), int(beam), int(n_cand)))
+
+
+def ctc_prefix_step(x, vocab, enc_len, r_prev, parent_slot, last_tok, parent_tok, prefix_len, n_live, cand,
+                    beam, n_cand, flags=0, psi=None, r_out=None, status=None, n_run=0):
+    """One fused launch of the per-step kernel (lazy state evaluation); see e2e_ctc_prefix_step in the header.
+    r_prev [U,Tmax,lanes_prev,2] -> (psi [U*B,C], r_out [U,Tmax,B,2])."""
+    t, u, vp = x.shape
+    _chk(x, F32, "x")
+    _chk(enc_len, I32, "enc_len", u)
+    _chk(r_prev, F32, "r_prev")
+    if r_prev.dim() != 4 or r_prev.shape[0] != u or r_prev.shape[1] != t or r_prev.shape[3] != 2:
+        raise ValueError("r_prev must be [U,Tmax,lanes,2]")
+    lanes_prev = r_prev.shape[2]
+    n = u * beam
+    _chk(parent_slot, I32, "parent_slot", n)
+    _chk(last_tok, I32, "last_tok", n)
+    _chk(parent_tok, I32, "parent_tok", n)
+    _chk(prefix_len, I32, "prefix_len", n)
+    _chk(n_live, I32, "n_live", u)
+    _chk(cand, I32, "cand", n * n_cand)
+    if psi is None:
+        psi = torch.empty((n, n_cand), dtype=F32, device=x.device)
+    if r_out is None:
+        r_out = torch.empty((u, t, beam, 2), dtype=F32, device=x.device)
+    _chk(psi, F32, "psi", n * n_cand)
+    _chk(r_out, F32, "r_out", u * t * beam * 2)
+    _chk(status, I32, "status", u)
+    L.check(L.load().e2e_ctc_prefix_step(
+        L.ptr(x), t, u, vp, int(vocab), L.ptr(enc_len), L.ptr(r_prev), lanes_prev,
+        L.ptr(parent_slot), L.ptr(last_tok), L.ptr(parent_tok), L.ptr(prefix_len), L.ptr(n_live), L.ptr(cand),
+        int(beam), int(n_cand), int(flags), L.ptr(psi), L.ptr(r_out), L.ptr(status), int(n_run), _stream()))
+    return psi, r_out
+
+
 def beam_candidates(att_logits, n_utts, beam, vocab, n_cand, n_live, att_stats, cand):
     _chk(att_logits, F32, "att_logits")
     ld = att_logits.stride(0) if att_logits.dim() == 2 else vocab
@@ -113,6 +149,7 @@ class BeamBuffers:
         self.parent_slot = z(u, b)
         self.parent_row = torch.arange(u * b, dtype=torch.int64, device=device).view(u, b)     # u*B + parent slot
         self.last_tok64 = z(u, b, dt=torch.int64)
+        self.parent_tok = torch.full((u, b), -1, dtype=I32, device=device)       # last token of each hypothesis' parent
         self.hist_tok, self.hist_parent = z(self.S, u, b), z(self.S, u, b)
         self.hist_score = z(self.S, u, b, dt=F32)
         self.fin_cap = int(fin_cap if fin_cap is not None else b)      # best-B closed hypotheses suffice
@@ -142,7 +179,7 @@ def beam_combine_prune(buf, att_logits, lm_logits, vocab, step, ctc_weight, lm_w
         L.ptr(buf.parent_slot),
         L.ptr(buf.hist_tok), L.ptr(buf.hist_parent), L.ptr(buf.hist_score),
         L.ptr(buf.fin_count), L.ptr(buf.fin_step), L.ptr(buf.fin_parent), L.ptr(buf.fin_sum), L.ptr(buf.fin_score),
-        buf.fin_cap, L.ptr(buf.status), int(n_run), L.ptr(buf.parent_row), L.ptr(buf.last_tok64), _stream()))
+        buf.fin_cap, L.ptr(buf.status), int(n_run), L.ptr(buf.parent_row), L.ptr(buf.last_tok64), L.ptr(buf.parent_tok), _stream()))
 
 
 def beam_finalize(buf, out_cap=None):

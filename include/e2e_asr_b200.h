@@ -112,6 +112,32 @@ int e2e_ctc_prefix_score(const float *x, int Tmax, int U, int Vp, int V, const i
                          const int *n_live, const int *cand, int B, int C, int flags,
                          float *psi, float *r_out, int *status, int n_run, void *stream);
 
+/* (2, beam-search form) ONE fused launch per decode step with LAZY state evaluation: the prefix
+ * state of every live hypothesis is brought up to date (it was left uncomputed when the hypothesis was only a
+ * candidate) and all B*C candidate extensions are scored.  Replaces CTCPrefixScore.cheap_compute (src/ctc.py:68-108)
+ * as src/decode.py:131 calls it, together with the state hand-over of src/decode.py:250-254: the recurrence
+ * (src/ctc.py:97-101) runs for the <= B hypotheses the beam kept instead of for all B*C candidates — same frames,
+ * same order, same fp32 operations, hence the same values — and the candidates only run psi (src/ctc.py:103).
+ *   r_prev      [U][Tmax][lanes_prev][2]  states of the PARENTS (previous step's r_out; the e2e_ctc_init_state
+ *               buffer with lanes_prev = 1 at steps 0 and 1)
+ *   parent_slot [U*B]  lane of hypothesis n's parent inside r_prev (e2e_beam_combine_prune's parent_slot; 0 at step 0)
+ *   last_tok    [U*B]  last token of hypothesis n (the token that extended the parent)
+ *   parent_tok  [U*B]  last token of the parent, -1 if the parent is the empty prefix (may be NULL while every
+ *               prefix_len <= 1)
+ *   prefix_len  [U*B]  len(g); all live hypotheses of an utterance have the same length (slot 0 is read).
+ *               prefix_len == 0: the hypothesis is the empty prefix, its state is r_prev itself, r_out is not written
+ *   n_live, cand, psi, status, n_run as e2e_ctc_prefix_score
+ *   r_out       [U][Tmax][B][2]  out: states of the live hypotheses, rows t >= max(1, len-1) - 1 (earlier rows are
+ *               log-zero by construction, never read back, and not written)
+ * flags: 0 or E2E_PREFIX_POLY_MATH (| E2E_PREFIX_POLY_ESTRIN).  Needs ceil(B/8) + ceil(B*C/32) <= 32 warps per
+ * utterance (e2e_ctc_prefix_step_supported). */
+int e2e_ctc_prefix_step_supported(int Vp, int B, int C);
+int e2e_ctc_prefix_step(const float *x, int Tmax, int U, int Vp, int V, const int *enc_len,
+                        const float *r_prev, int lanes_prev,
+                        const int *parent_slot, const int *last_tok, const int *parent_tok, const int *prefix_len,
+                        const int *n_live, const int *cand, int B, int C, int flags,
+                        float *psi, float *r_out, int *status, int n_run, void *stream);
+
 /* (3a) Attention log-softmax statistics + CTC candidate pre-pruning.  Replaces
  * F.log_softmax(cur_prob) and cur_prob.topk(ctc_beam_size) (src/decode.py:122,129-130).
  *   att_logits [U*B][ld] decoder outputs (char_trans), row pitch ld >= V
@@ -141,6 +167,8 @@ int e2e_beam_candidates(const float *att_logits, int ld, int U, int B, int V, in
  * (<= 0: all U).
  *   parent_row, last_tok64 [U][B] int64 (either may be NULL): u*B + parent_slot and last_tok again, in the
  *   index type the caller's state gathers / embedding look-ups take, so that no conversion kernels are needed.
+ *   parent_tok [U][B] int32 (may be NULL): the last token of each new hypothesis' PARENT (-1 for the empty prefix) —
+ *   what e2e_ctc_prefix_step needs to tell a repeated token (src/ctc.py:89-91) when it builds the survivor's state.
  *   lm_logits may be NULL iff E2E_BEAM_USE_LM is clear; cand/psi iff E2E_BEAM_USE_CTC is clear. */
 int e2e_beam_combine_prune(const float *att_logits, int ld_att, const float *att_stats,
                            const float *lm_logits, int ld_lm,
@@ -154,7 +182,7 @@ int e2e_beam_combine_prune(const float *att_logits, int ld_att, const float *att
                            int *hist_tok, int *hist_parent, float *hist_score,
                            int *fin_count, int *fin_step, int *fin_parent, float *fin_sum, float *fin_score,
                            int fin_cap, int *status, int n_run,
-                           long long *parent_row, long long *last_tok64, void *stream);
+                           long long *parent_row, long long *last_tok64, int *parent_tok, void *stream);
 
 /* Final N-best selection + back-tracking.  Replaces src/decode.py:180-183 and
  * Hypothesis.outIndex (src/decode.py:279-281): closed hypotheses followed by the last

@@ -207,6 +207,131 @@ def test_prefix_score_midsize_vocab_rows(cuda):
 
 
 # ----------------------------------------------------------------------------------------------
+# (2) fused per-step kernel with lazy state evaluation (e2e_ctc_prefix_step): the same beam-search-shaped chains
+# ----------------------------------------------------------------------------------------------
+def _chain_lazy(cuda, rng, n_utts, t_lens, vocab, beam, n_cand, n_steps, flags=0, n_run=0, drop_live=False):
+    """Per step: psi of every (hypothesis, candidate) against the oracle's cheap_compute, and the state the kernel
+    built for every live hypothesis (rows from max(1, len-1) - 1 on) against the oracle's state of that prefix."""
+    ops, L = _ops()
+    from oracle import c_oracle as CO
+    t_max = max(t_lens)
+    post = posteriors(rng, n_utts, t_max, vocab)
+    vp = ops.padded_vocab(vocab)
+    x = np.full((t_max, n_utts, vp), LOGZERO, np.float32)
+    x[:, :, :vocab] = post.transpose(1, 0, 2)
+    for u, n in enumerate(t_lens):
+        x[n:, u] = LOGZERO
+    xd = torch.from_numpy(x).to(cuda)
+    enc_len = torch.tensor(t_lens, dtype=torch.int32, device=cuda)
+    r_init = ops.ctc_init_state(xd, enc_len)                                   # [U,T,1,2]
+    beams = [[([], CO.blank_state(post[u, :t_lens[u]]), 0, -1)] for u in range(n_utts)]     # (prefix, state, parent slot, parent tok)
+    status = torch.zeros(n_utts, dtype=torch.int32, device=cuda)
+    r_bufs = [torch.empty((n_utts, t_max, beam, 2), device=cuda) for _ in range(2)]
+    worst = 0.0
+    n_chk = n_utts if n_run <= 0 else n_run
+    for step in range(n_steps):
+        n_live = torch.tensor([len(b) for b in beams], dtype=torch.int32)
+        cand = np.zeros((n_utts, beam, n_cand), np.int32)
+        last = np.zeros((n_utts, beam), np.int32)
+        plen = np.zeros((n_utts, beam), np.int32)
+        pslot = np.zeros((n_utts, beam), np.int32)
+        ptok = np.full((n_utts, beam), -1, np.int32)
+        for u in range(n_utts):
+            for b, (g, _, ps, pt) in enumerate(beams[u]):
+                cs = rng.permutation(vocab)[:n_cand].astype(np.int32)
+                if (step + b) % 2 == 0 and 1 not in cs:
+                    cs[int(rng.integers(n_cand))] = 1                          # the <eos> override
+                if g and (step + b) % 3 == 0 and g[-1] not in cs:
+                    cs[int(rng.integers(n_cand))] = g[-1]                      # a repeated token among the candidates
+                if len(set(cs.tolist())) < n_cand:
+                    cs = rng.permutation(vocab)[:n_cand].astype(np.int32)
+                cand[u, b], last[u, b], plen[u, b], pslot[u, b], ptok[u, b] = cs, (g[-1] if g else 0), len(g), ps, pt
+        r_prev = r_init if step <= 1 else r_bufs[(step - 1) % 2]
+        r_out = r_bufs[step % 2]
+        r_out.fill_(float("nan"))
+        to = lambda a: torch.from_numpy(a.reshape(-1)).to(cuda)
+        psi, _ = ops.ctc_prefix_step(xd, vocab, enc_len, r_prev, to(pslot), to(last), to(ptok), to(plen), n_live.to(cuda),
+                                     torch.from_numpy(cand.reshape(-1, n_cand)).to(cuda), beam, n_cand, flags,
+                                     r_out=r_out, status=status, n_run=n_run)
+        psi = psi.cpu().numpy().reshape(n_utts, beam, n_cand)
+        r_host = r_out.cpu().numpy()                                           # [U,T,B,2]
+        new_beams = []
+        for u in range(n_utts):
+            n = t_lens[u]
+            outs = []
+            for b, (g, st, _, _) in enumerate(beams[u]):
+                p_o, r_o = CO.extend(post[u, :n], len(g), g[-1] if g else 0, st, cand[u, b].tolist())
+                if u < n_chk:
+                    worst = max(worst, assert_prefix_close(psi[u, b], p_o, "psi step %d utt %d slot %d" % (step, u, b)))
+                    if step >= 1:       # the hypothesis' own state, as the kernel rebuilt it from its parent's
+                        first = max(1, step - 1) - 1
+                        worst = max(worst, assert_prefix_close(r_host[u, first:n, b], st[first:], "state step %d utt %d slot %d" % (step, u, b)))
+                outs.append((g, r_o))
+            picks = [(b, j) for b in range(len(outs)) for j in range(n_cand)]
+            n_keep = beam if not (drop_live and u % 3 == 1) else max(1, beam - 1 - (step % 2))
+            keep = [picks[i] for i in rng.permutation(len(picks))[:n_keep]]
+            if step % 2 == 1:                                                  # make sure repeated tokens survive sometimes
+                for b, (g, _) in enumerate(outs):
+                    if g and g[-1] in cand[u, b].tolist():
+                        keep[0] = (b, cand[u, b].tolist().index(g[-1]))
+                        break
+            nb = []
+            for b, j in keep:
+                g, r_o = outs[b]
+                nb.append((g + [int(cand[u, b, j])], np.ascontiguousarray(r_o[j]), b, (g[-1] if g else -1)))
+            new_beams.append(nb)
+        beams = new_beams
+    assert int(status.abs().sum()) == 0
+    return worst
+
+
+@pytest.mark.parametrize("mode", ["lut", "poly", "poly_estrin"])
+def test_prefix_step_cfg2_shape(cuda, mode):
+    _, L = _ops()
+    fl = {"lut": 0, "poly": L.PREFIX_POLY_MATH, "poly_estrin": L.PREFIX_POLY_MATH | L.PREFIX_POLY_ESTRIN}[mode]
+    rng = np.random.default_rng(12)
+    w = _chain_lazy(cuda, rng, n_utts=5, t_lens=[180, 37, 96, 64, 181], vocab=31, beam=8, n_cand=12, n_steps=24, flags=fl, drop_live=True)
+    print("fused step, cfg2 shape: max |gpu-oracle| = %.3g (math=%s)" % (w, mode))
+
+
+def test_prefix_step_cfg1_shape(cuda):
+    rng = np.random.default_rng(11)
+    w = _chain_lazy(cuda, rng, n_utts=3, t_lens=[250, 249, 100], vocab=31, beam=2, n_cand=3, n_steps=14)
+    print("fused step, cfg1 shape: max |gpu-oracle| = %.3g" % w)
+
+
+def test_prefix_step_longform_beam16(cuda):
+    rng = np.random.default_rng(14)
+    w = _chain_lazy(cuda, rng, n_utts=2, t_lens=[875, 640], vocab=31, beam=16, n_cand=24, n_steps=6)
+    print("fused step, cfg4 shape: max |gpu-oracle| = %.3g" % w)
+
+
+def test_prefix_step_large_vocab_gather(cuda):
+    rng = np.random.default_rng(15)
+    w = _chain_lazy(cuda, rng, n_utts=2, t_lens=[60, 45], vocab=10000, beam=8, n_cand=12, n_steps=6)
+    print("fused step, cfg3 shape (gather variant): max |gpu-oracle| = %.3g" % w)
+
+
+def test_prefix_step_midsize_vocab_and_short_utterances(cuda):
+    rng = np.random.default_rng(16)
+    _chain_lazy(cuda, rng, n_utts=4, t_lens=[50, 41, 3, 1], vocab=200, beam=3, n_cand=4, n_steps=1)
+    _chain_lazy(cuda, rng, n_utts=3, t_lens=[50, 41, 7], vocab=200, beam=3, n_cand=4, n_steps=5)
+    _chain_lazy(cuda, rng, n_utts=3, t_lens=[17, 16, 33], vocab=31, beam=4, n_cand=6, n_steps=15, drop_live=True)
+
+
+@pytest.mark.parametrize("beam,n_cand", [(8, 12), (4, 6)])
+def test_prefix_step_bench_sized_launch(cuda, beam, n_cand):
+    """>= 296 utterances in one launch: the 16-frame-tile instantiations the bench's machine-filling launches run,
+    incl. the fixed-shape (Vp = 32) kernel; n_run < U leaves the tail of the batch untouched."""
+    rng = np.random.default_rng(23)
+    n_utts = 700
+    t_lens = [int(t) for t in rng.integers(5, 48, n_utts)]
+    t_lens[0], t_lens[1], t_lens[2] = 83, 5, 16
+    w = _chain_lazy(cuda, rng, n_utts=n_utts, t_lens=t_lens, vocab=31, beam=beam, n_cand=n_cand, n_steps=5, n_run=640)
+    print("fused step, bench-sized launch B=%d: max |gpu-oracle| = %.3g" % (beam, w))
+
+
+# ----------------------------------------------------------------------------------------------
 # drop-in CTCPrefixScore class (src/ctc.py interface)
 # ----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("t_len,vocab,n_cand", [(1, 31, 3), (2, 31, 3), (7, 31, 12), (60, 31, 12), (50, 200, 12)])

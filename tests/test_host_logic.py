@@ -221,7 +221,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     import json, os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-           "--cpu-sample", "2", "--cpu-frames", "40", "--cpu-procs", "2"]
+           "--cpu-sample", "2", "--cpu-frames", "40", "--cpu-procs", "2", "--as-shipped-sample", "1"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
@@ -229,8 +229,9 @@ def test_bench_reference_arm_prints_the_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "utts/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "utts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 2 and d["gpu_launches"] == 0
-    assert "median" not in d["cpu_baseline"]["sample"]                      # 40 frames is not the workload's median
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 2 and d["gpu_launches"] == 0
+    assert "unmodified reference" in d["cpu_baseline"]["sample"] and "quantile" not in d["cpu_baseline"]["sample"]   # fixed-length smoke sample
+    assert d["cpu_baseline"]["as_shipped"]["n_jobs"] == 4 and d["cpu_baseline"]["as_shipped"]["value"] > 0
     quiet = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert quiet.returncode == 0 and quiet.stdout.strip() == ""
 

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--poly", type=int, default=0, help="1: MUFU.EX2 + polynomial log-add-exp (Horner), 2: the same, pairwise (Estrin)")
     ap.add_argument("--skip-dead", type=int, default=0)
     ap.add_argument("--ragged", type=int, default=0)
+    ap.add_argument("--lazy", type=int, default=0, help="1: the fused per-step kernel with lazy state evaluation (e2e_ctc_prefix_step)")
     a = ap.parse_args()
     from e2e_asr_pytorch_b200 import ops, _lib as L
     dev = torch.device("cuda:0")
@@ -62,8 +63,28 @@ def main():
     lane0 = torch.randint(0, C, (U * B,), generator=g).to(torch.int32).to(dev)      # only slot 0 lanes are valid after step 0
     ops.ctc_prefix_score(x, V, enc_len, bufs[0], lane0, last, plen, n_live, cand, B, C, 0, psi=psi, r_out=bufs[1], status=status)
     cur = 1
+    if a.lazy:
+        # state buffers hold the B live hypotheses only; every hypothesis' parent is a random slot of the previous buffer
+        bufs = [torch.empty((U, T, B, 2), device=dev) for _ in range(2)]
+        pslot = torch.randint(0, B, (U * B,), generator=g).to(torch.int32).to(dev)
+        ptok = torch.randint(2, V, (U * B,), generator=g).to(torch.int32).to(dev)
+        one = torch.ones_like(plen)
+        ops.ctc_prefix_step(x, V, enc_len, r0, torch.zeros_like(pslot), last, None, one, n_live, cand, B, C, 0,
+                            psi=psi, r_out=bufs[0], status=status)
+        ops.ctc_prefix_step(x, V, enc_len, bufs[0], pslot, last, ptok, one + 1, n_live, cand, B, C, 0,
+                            psi=psi, r_out=bufs[1], status=status)
+        lflags = flags & ~(L.PREFIX_SKIP_DEAD_ROWS)
 
     def launch():
+        nonlocal cur
+        if a.lazy:
+            ops.ctc_prefix_step(x, V, enc_len, bufs[cur], pslot, last, ptok, plen, n_live, cand, B, C, lflags,
+                                psi=psi, r_out=bufs[1 - cur], status=status)
+            cur = 1 - cur
+            return
+        _launch_eager()
+
+    def _launch_eager():
         nonlocal cur
         ops.ctc_prefix_score(x, V, enc_len, bufs[cur], lane, last, plen, n_live, cand, B, C, flags,
                              psi=psi, r_out=bufs[1 - cur], status=status)
@@ -87,7 +108,7 @@ def main():
     except Exception:
         pass
     gbs = units * bpu / (ms.mean() * 1e-3) / 1e9
-    print(json.dumps({"kernel": "prefix_score", "utts": U, "frames": T, "vocab": V, "beam": B, "cand": C, "plen": a.plen,
+    print(json.dumps({"kernel": "prefix_step_lazy" if a.lazy else "prefix_score", "utts": U, "frames": T, "vocab": V, "beam": B, "cand": C, "plen": a.plen,
                       "math": "mufu" if a.fast else ("libm" if a.libm else (["lut", "poly", "poly_estrin"][a.poly])), "skip_dead_rows": a.skip_dead, "ms_mean": float(ms.mean()), "ms_min": float(ms.min()),
                       "cand_frames": units, "cand_frames_per_s": units / (ms.mean() * 1e-3), "bytes_per_cand_frame": bpu,
                       "algorithmic_GBps": gbs, "frac_of_measured_hbm_peak": gbs / peak, "status": int(status.sum().item()),
