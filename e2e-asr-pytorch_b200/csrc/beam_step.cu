@@ -370,7 +370,55 @@ beam_finalize_kernel(const FinalParams p)
     if (threadIdx.x == 0) p.out_n[u] = total < B ? total : B;
 }
 
+// ---------------------------------------------------------------------------------------------
+// ragged N-best pack: one CTA per decoded utterance, straight from beam_finalize's outputs into the
+// rank's gather buffer (shard.py: headers | tokens | score bits)
+// ---------------------------------------------------------------------------------------------
+struct PackParams {
+    int U, B, cap_in;
+    const int *tok; const float *score; const int *len; const float *avg; const int *n;
+    const int *slot; const long long *tok_off; const int *cap;
+    int *hdr, *tok_out, *sc_out;
+};
+
+__global__ void __launch_bounds__(256)
+nbest_pack_kernel(const PackParams p)
+{
+    const int u = blockIdx.x, B = p.B;
+    const int cap = p.cap[u];
+    int *hdr = p.hdr + (long long)p.slot[u] * (1 + 2 * B);
+    if (threadIdx.x == 0) hdr[0] = p.n[u];
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        hdr[1 + b] = p.len[u * B + b];
+        hdr[1 + B + b] = __float_as_int(p.avg[u * B + b]);
+    }
+    const long long base = p.tok_off[u];
+    for (int i = threadIdx.x; i < B * cap; i += blockDim.x) {
+        const int b = i / cap, k = i - b * cap;
+        const long long src = ((long long)u * B + b) * p.cap_in + k;
+        const bool have = k < p.cap_in;
+        p.tok_out[base + i] = have ? p.tok[src] : 0;
+        p.sc_out[base + i] = have ? __float_as_int(p.score[src]) : 0;
+    }
+}
+
 }  // namespace e2e
+
+extern "C" int e2e_nbest_pack_ragged(int U, int B, int cap_in, const int *tok, const float *score, const int *len,
+                                     const float *avg, const int *n, const int *slot, const long long *tok_off,
+                                     const int *cap, int *hdr, int *tok_out, int *sc_out, void *stream)
+{
+    using namespace e2e;
+    if (!tok || !score || !len || !avg || !n || !slot || !tok_off || !cap || !hdr || !tok_out || !sc_out)
+        return set_error(E2E_ERR_ARG, "e2e_nbest_pack_ragged: null pointer");
+    if (U <= 0 || B <= 0 || cap_in <= 0) return set_error(E2E_ERR_ARG, "e2e_nbest_pack_ragged: bad size");
+    PackParams p;
+    p.U = U; p.B = B; p.cap_in = cap_in; p.tok = tok; p.score = score; p.len = len; p.avg = avg; p.n = n;
+    p.slot = slot; p.tok_off = tok_off; p.cap = cap; p.hdr = hdr; p.tok_out = tok_out; p.sc_out = sc_out;
+    nbest_pack_kernel<<<U, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    count_launch();
+    return check_launch("e2e_nbest_pack_ragged");
+}
 
 extern "C" int e2e_beam_candidates(const float *att_logits, int ld, int U, int B, int V, int C,
                                    const int *n_live, float *att_stats, int *cand, void *stream)

@@ -197,6 +197,11 @@ class BeamDecoder(nn.Module):
         (tokens, scores, lens, avg, n) CPU tensors instead (used by the sharded driver)."""
         if not audio_feature.is_cuda:
             raise L.E2EError("BeamDecoder has no CPU path: move the features and the decoder to a CUDA device")
+        # the hand-written kernels are enqueued on the CURRENT device's current stream: make the features' device current
+        with torch.cuda.device(audio_feature.device):
+            return self._decode_batch(audio_feature, feature_len, return_arrays)
+
+    def _decode_batch(self, audio_feature, feature_len, return_arrays):
         dev = audio_feature.device
         n_utts = audio_feature.shape[0]
         beam = self.beam_size

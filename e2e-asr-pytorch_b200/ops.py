@@ -199,6 +199,19 @@ def beam_finalize(buf, out_cap=None):
     return tok, sc, ln, avg, n
 
 
+def nbest_pack_ragged(tok, sc, ln, avg, n, slot, tok_off, cap, hdr, tok_out, sc_out):
+    """Device N-best (beam_finalize's outputs, any row pitch) -> the rank's ragged gather buffer; see
+    e2e_nbest_pack_ragged.  slot / cap int32 [U], tok_off int64 [U]; hdr / tok_out / sc_out int32 views of the buffer."""
+    u, beam, cap_in = tok.shape
+    _chk(tok, I32, "tok"); _chk(sc, F32, "sc"); _chk(ln, I32, "ln", u * beam); _chk(avg, F32, "avg", u * beam); _chk(n, I32, "n", u)
+    _chk(slot, I32, "slot", u); _chk(tok_off, torch.int64, "tok_off", u); _chk(cap, I32, "cap", u)
+    _chk(hdr, I32, "hdr"); _chk(tok_out, I32, "tok_out"); _chk(sc_out, I32, "sc_out")
+    if u == 0:
+        return
+    L.check(L.load().e2e_nbest_pack_ragged(u, beam, cap_in, L.ptr(tok), L.ptr(sc), L.ptr(ln), L.ptr(avg), L.ptr(n), L.ptr(slot),
+                                          L.ptr(tok_off), L.ptr(cap), L.ptr(hdr), L.ptr(tok_out), L.ptr(sc_out), _stream()))
+
+
 def attention_loc_step(key, query, loc_feat, enc_len, w_proj, w_energy, b_energy, temperature, beam, out=None):
     """Fused location-aware attention energies + masked softmax: key [U,T,A], query [n,A],
     loc_feat [n,K,T] (conv of the previous alignment) -> attn [n,T]."""

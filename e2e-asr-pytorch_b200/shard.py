@@ -7,9 +7,12 @@ so here whole utterances are dealt to ranks (one process per GPU), every rank
 decodes its shard with the batched device beam search, and ONE all-gather of a
 packed int32 N-best buffer (NCCL over NVLink/NVSwitch; gloo in the CPU tests)
 gives every rank the full result in the original utterance order.  Nothing else
-crosses GPUs.  Two buffer formats: rectangular rows padded to the set's longest
-utterance (pack_nbest, what bench.py gathers), and the ragged one decode_sharded
-uses (pack_nbest_ragged: ~4.5x smaller for a dev-clean-like set).
+crosses GPUs.  The buffer is RAGGED (every rank derives the same layout from the
+length list: no ids travel, nothing is padded to the set's longest utterance; ~4.5x
+smaller than rectangular rows for a dev-clean-like set) and is packed ON THE DEVICE
+from the finalize kernel's outputs (RaggedPacker -> e2e_nbest_pack_ragged), gathered
+where it lies and read back once into pinned host memory.  pack_nbest (rectangular)
+and pack_nbest_ragged (CPU) remain for the gloo tests and as cross-checks.
 """
 import numpy as np
 import torch
@@ -222,15 +225,68 @@ def unpack_nbest_ragged(buf, shards, lengths, beam, max_len_ratio, size):
     return tok, sc_bits.view(torch.float32), ln, avg, n
 
 
+class RaggedPacker:
+    """Device-side packing of one rank's ragged buffer: the layout tables (slot, token offset, capacity per utterance)
+    live on the device, and the N-best of every decoded batch goes from ``beam_finalize``'s outputs straight into the
+    buffer with one small kernel (``e2e_nbest_pack_ragged``) — no host copy, no CPU temporaries."""
+
+    def __init__(self, shard_ids, lengths, beam, max_len_ratio, size, device):
+        caps, total = ragged_layout(shard_ids, lengths, beam, max_len_ratio)
+        if total > size:
+            raise ValueError("ragged N-best buffer too small")
+        self.beam, self.size, self.device = beam, int(size), device
+        self.n_shard = len(caps)
+        self.hdr_len = self.n_shard * (1 + 2 * beam)
+        self.tok_len = int(beam * caps.sum())
+        off = beam * (np.cumsum(caps) - caps)                                  # first token element of every layout slot
+        self._slot_of = {int(u): k for k, u in enumerate(shard_ids)}
+        self._caps, self._off = caps, off
+        self.buf = torch.zeros(self.size, dtype=torch.int32, device=device)
+        self._tables = {}
+
+    def reset(self):
+        """Headers back to 'not decoded' (n = -1); the token / score sections are overwritten by the packs."""
+        self.buf[:self.hdr_len].view(self.n_shard, -1)[:, 0] = -1
+
+    def pack(self, utt_ids, tok, sc, ln, avg, n):
+        """N-best of the decoded utterances ``utt_ids`` (device tensors, rows in this order) -> their slots."""
+        from . import ops
+        key = tuple(int(u) for u in utt_ids)
+        tab = self._tables.get(key)
+        if tab is None:
+            slots = np.array([self._slot_of[u] for u in key], dtype=np.int64)
+            tab = (torch.as_tensor(slots.astype(np.int32), device=self.device),
+                   torch.as_tensor(self._off[slots].astype(np.int64), device=self.device),
+                   torch.as_tensor(self._caps[slots].astype(np.int32), device=self.device))
+            self._tables[key] = tab
+        hdr = self.buf[:self.hdr_len]
+        t0 = self.hdr_len
+        ops.nbest_pack_ragged(tok.contiguous(), sc.contiguous(), ln.contiguous(), avg.contiguous(), n.contiguous(), tab[0], tab[1], tab[2],
+                              hdr, self.buf[t0:t0 + self.tok_len], self.buf[t0 + self.tok_len:t0 + 2 * self.tok_len])
+        return self.buf
+
+
 def ragged_size(shards, lengths, beam, max_len_ratio):
     """The common buffer size: the largest shard's (every rank computes the same number from the same plan)."""
     return max([ragged_layout(ids, lengths, beam, max_len_ratio)[1] for ids in shards] + [1])
 
 
 def gather_nbest(local_buf, device=None):
-    """The one collective of the sharded decode: all-gather of the packed buffers (same shape
-    on every rank).  Returns the concatenation of all ranks' buffers on the CPU."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+    """The one collective of the sharded decode: all-gather of the packed buffers (same shape on every rank).
+    Returns the concatenation of all ranks' buffers on the host.  A CUDA ``local_buf`` (RaggedPacker) is gathered where
+    it lies and read back ONCE into pinned host memory; a CPU buffer (gloo tests, legacy CPU packing) is sent as it is."""
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if local_buf.is_cuda:
+        recv = local_buf
+        if multi:
+            recv = torch.empty((dist.get_world_size() * local_buf.shape[0],) + tuple(local_buf.shape[1:]),
+                               dtype=local_buf.dtype, device=local_buf.device)
+            dist.all_gather_into_tensor(recv, local_buf.contiguous())
+        host = torch.empty(recv.shape, dtype=recv.dtype, pin_memory=True)     # the caching host allocator reuses the block
+        host.copy_(recv, non_blocking=True)
+        torch.cuda.current_stream(local_buf.device).synchronize()
+        return host
+    if not multi:
         return local_buf
     world = dist.get_world_size()
     send = local_buf.to(device) if device is not None else local_buf
@@ -243,25 +299,37 @@ def decode_sharded(decode_fn, lengths, beam, max_len_ratio, rank=0, world_size=1
                    max_utts=512, max_padded_frames=None):
     """Decode utterances 0..len(lengths)-1 across ``world_size`` ranks.
 
-    ``decode_fn(batch_ids) -> (tok, sc, ln, avg, n)`` CPU tensors for the utterances in
-    ``batch_ids`` (what ``BeamDecoder.decode_batch(..., return_arrays=True)`` returns).
+    ``decode_fn(batch_ids) -> (tok, sc, ln, avg, n)`` for the utterances in ``batch_ids``: what
+    ``BeamDecoder.decode_batch(..., return_arrays="device")`` returns (CUDA tensors: packed on the device, gathered over
+    NCCL, one read-back) or ``return_arrays=True`` (CPU tensors: packed on the host — the gloo tests).
     Every rank returns the full (tok, sc, ln, avg, n) arrays in utterance order."""
     lengths = np.asarray(lengths)
-    n_total = len(lengths)
     shards = plan_shards(lengths, world_size, max_len_ratio)
     size = ragged_size(shards, lengths, beam, max_len_ratio)
     mine = shards[rank]
-    parts, ids = [], []
+    parts, ids, packer = [], [], None
     for batch in make_batches(mine, lengths, max_utts, max_padded_frames):
-        parts.append(decode_fn(batch))
+        part = decode_fn(batch)
+        if part[0].is_cuda:
+            if packer is None:
+                packer = RaggedPacker(mine, lengths, beam, max_len_ratio, size, part[0].device)
+                packer.reset()
+            packer.pack(batch, *part)
+        else:
+            parts.append(part)
         ids.extend(batch)
-    if parts:
-        width = max(p[0].shape[2] for p in parts)
-        pad = lambda a: torch.nn.functional.pad(a, (0, width - a.shape[2]))
-        tok = torch.cat([pad(p[0]) for p in parts]); sc = torch.cat([pad(p[1]) for p in parts])
-        ln = torch.cat([p[2] for p in parts]); avg = torch.cat([p[3] for p in parts]); n = torch.cat([p[4] for p in parts])
+    if packer is not None:
+        local = packer.buf
     else:
-        tok = torch.zeros((0, beam, 1), dtype=torch.int32); sc = torch.zeros((0, beam, 1))
-        ln = torch.zeros((0, beam), dtype=torch.int32); avg = torch.zeros((0, beam)); n = torch.zeros((0,), dtype=torch.int32)
-    local = pack_nbest_ragged(ids, tok, sc, ln, avg, n, mine, lengths, beam, max_len_ratio, size)
+        if parts:
+            width = max(p[0].shape[2] for p in parts)
+            pad = lambda a: torch.nn.functional.pad(a, (0, width - a.shape[2]))
+            tok = torch.cat([pad(p[0]) for p in parts]); sc = torch.cat([pad(p[1]) for p in parts])
+            ln = torch.cat([p[2] for p in parts]); avg = torch.cat([p[3] for p in parts]); n = torch.cat([p[4] for p in parts])
+        else:
+            tok = torch.zeros((0, beam, 1), dtype=torch.int32); sc = torch.zeros((0, beam, 1))
+            ln = torch.zeros((0, beam), dtype=torch.int32); avg = torch.zeros((0, beam)); n = torch.zeros((0,), dtype=torch.int32)
+        local = pack_nbest_ragged(ids, tok, sc, ln, avg, n, mine, lengths, beam, max_len_ratio, size)
+        if device is not None and len(mine) == 0:
+            local = local.to(device)
     return unpack_nbest_ragged(gather_nbest(local, device), shards, lengths, beam, max_len_ratio, size)

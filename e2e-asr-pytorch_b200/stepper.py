@@ -310,7 +310,9 @@ class BatchedStepper:
             if hasattr(layer, "conv_split_format"):
                 layer.conv_split_format = self.vgg_split
         if n_utts == 1:
-            enc, enc_len = enc_mod(feats, lens)
+            # one utterance: the plain module call, on the valid frames only — zero padding would otherwise reach the
+            # backward LSTM direction (the reference's batch-1 call is never padded, bin/test_asr.py:159-167)
+            enc, enc_len = enc_mod(feats[:, :int(lens[0])], lens)
         elif self.split_conv and feats.is_cuda and hasattr(enc_mod, "forward_ragged_packed") and enc_mod.packed_supported():
             # device path: split convolutions, packed frames, persistent recurrent kernel (model.py)
             enc_mod.split_conv = True

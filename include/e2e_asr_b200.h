@@ -196,6 +196,18 @@ int e2e_beam_finalize(int U, int B, const int *max_len,
                       int *out_tok, float *out_score, int *out_len, float *out_avg, int *out_n,
                       int out_cap, void *stream);
 
+/* (e) Ragged N-best pack for the one all-gather of the utterance-sharded decode (it takes the place of
+ * the per-utterance result lists joblib returns to the parent process, bin/test_asr.py:138-139): the N-best of U
+ * decoded utterances (e2e_beam_finalize's outputs, row pitch cap_in) go straight into the rank's gather buffer
+ *   hdr     [n_shard][1 + 2B]  per layout slot: n, len_0..len_{B-1}, bits(avg_0)..bits(avg_{B-1})
+ *   tok_out [sum_u B*cap_u]    per utterance B hypotheses x cap_u tokens (cap_u = ceil(L_u * max_len_ratio) + 1)
+ *   sc_out  the same for the per-token score bits
+ * slot[u]: layout slot of decoded row u; tok_off[u]: its first element in tok_out / sc_out; cap[u]: its cap_u.
+ * Every rank derives the same layout from the length list, so no ids travel (shard.py). */
+int e2e_nbest_pack_ragged(int U, int B, int cap_in, const int *tok, const float *score, const int *len,
+                          const float *avg, const int *n, const int *slot, const long long *tok_off,
+                          const int *cap, int *hdr, int *tok_out, int *sc_out, void *stream);
+
 /* (next) Fused location-aware attention energies + masked softmax for one
  * decode step.  Replaces LocationAwareAttention.forward minus the convolution
  * (src/module.py:1163-1168) and BaseAttention._attend minus the context product

@@ -91,6 +91,31 @@ def _expand(parent, top_ids, top_vals, dec_state, att_map, lm_state, ctc_state, 
     return None, children
 
 
+def blend_ctc(score, cands, psi, parent_psi, ctc_weight):
+    """decode.py:134-141: CTC prefix deltas spread over the vocabulary (LOG_ZERO elsewhere), blended with the
+    attention log-probs [1,V]; token 0 is blocked after blending.  Returns a NEW tensor (``score`` keeps the pure
+    attention values the <eos> test looks at)."""
+    delta = torch.FloatTensor(psi - parent_psi).to(score.device)
+    spread = torch.zeros_like(score).data.fill_(LOG_ZERO)
+    for j, c in enumerate(cands):
+        spread[0, c] = delta[j]
+    score = (1 - ctc_weight) * score + ctc_weight * spread
+    score[0, 0] = LOG_ZERO
+    return score
+
+
+def add_lm(score, lm_out, lm_weight):
+    """decode.py:144-151: in-place add of the weighted LM log-probs (lm_out: logits [1,V])."""
+    score += lm_weight * lm_out.log_softmax(dim=-1)
+    return score
+
+
+def prune(pool, beam_size):
+    """decode.py:175-176: stable sort by mean score, best ``beam_size`` kept; ties keep (parent, rank) order."""
+    pool.sort(key=lambda b: b.mean_score(), reverse=True)
+    return pool[:beam_size]
+
+
 def decode_utterance(asr, feat, feat_len, beam_size, min_len_ratio, max_len_ratio,
                      lm=None, lm_weight=0.0, ctc_weight=0.0, trace=None, scorer_cls=None):
     """Joint CTC/attention(+LM) beam search of ONE utterance on CPU.
@@ -150,19 +175,14 @@ def decode_utterance(asr, feat, feat_len, beam_size, min_len_ratio, max_len_rati
                 cands = cand_t.cpu().tolist()
                 psi, new_state = scorer.cheap_compute(hyp.ids, hyp.ctc_state, cands)
                 stats["cand_frames"] += len(cands) * scorer.input_length
-                delta = torch.FloatTensor(psi - hyp.ctc_prob).to(device)
-                spread = torch.zeros_like(score).data.fill_(LOG_ZERO)
-                for j, c in enumerate(cands):
-                    spread[0, c] = delta[j]
-                score = (1 - ctc_weight) * score + ctc_weight * spread
-                score[0, 0] = LOG_ZERO
+                score = blend_ctc(score, cands, psi, hyp.ctc_prob, ctc_weight)
                 if rec is not None:
                     rec.update(cands=list(cands), psi=np.array(psi), parent_psi=np.float32(hyp.ctc_prob),
                                r_prev=np.array(hyp.ctc_state))
             if use_lm:
                 lm_out, lm_state = lm(tok_prev.unsqueeze(1), torch.ones([1]), hidden=lm_prev)
                 lm_out = lm_out.squeeze(0)
-                score += lm_weight * lm_out.log_softmax(dim=-1)
+                score = add_lm(score, lm_out, lm_weight)
                 if rec is not None:
                     rec["lm_logits"] = lm_out.detach().clone()
 
@@ -178,8 +198,7 @@ def decode_utterance(asr, feat, feat_len, beam_size, min_len_ratio, max_len_rati
                 if beam_size == 1:
                     return done
             pool.extend(children)
-        pool.sort(key=lambda b: b.mean_score(), reverse=True)     # stable; ties keep (parent, rank) order
-        live = pool[:beam_size]
+        live = prune(pool, beam_size)
 
     done += live
     done.sort(key=lambda b: b.mean_score(), reverse=True)
