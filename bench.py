@@ -36,12 +36,25 @@ METRIC = "beam-8+LM joint CTC/attn decode utts/sec"
 MEDIAN_NOTE = ", the workload's median length"
 
 
+def kernel_source_sha():
+    """Hash of the sources the prefix-score kernels are built from: an ncu capture is only quoted while it matches."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("prefix_lazy.cu", "prefix_score.cu", "common.cuh", "softplus_poly.inc", "softplus_lut.inc"):
+        with open(os.path.join(ROOT, "e2e-asr-pytorch_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def load_traffic():
-    """DRAM bytes per prefix-score launch, averaged over the launches of one timed pass of this same
-    command under ncu (profiles/r01_prefix_traffic_inbench.json; tools/summarize_ncu.py made it)."""
+    """DRAM bytes per prefix-score launch, averaged over the launches of one timed pass of this same command under ncu
+    (profiles/r02_prefix_traffic_inbench.json; tools/summarize_ncu.py made it).  The file carries the hash of the kernel
+    sources it was captured from: a capture of another kernel version is not quoted (null)."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_prefix_traffic_inbench.json")))
-        return float(d["dram_bytes_per_launch"]), "profiles/r01_prefix_traffic_inbench.json (ncu dram__bytes_read+write, mean of 660 launches)"
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_prefix_traffic_inbench.json")))
+        if d.get("kernel_source_sha") != kernel_source_sha():
+            return None, "profiles/r02_prefix_traffic_inbench.json is of another kernel version (stale): not quoted"
+        return float(d["dram_bytes_per_launch"]), "profiles/r02_prefix_traffic_inbench.json (ncu dram__bytes_read+write, mean over the launches of a pass)"
     except Exception:
         return None, None
 
@@ -132,6 +145,34 @@ def make_features(ids, lengths, pin):
     return synth.padded_batch(ids, [lengths[i] for i in ids], pin=pin)
 
 
+def golden_parity(tok, sc, ln, avg, nn, tie_tol=5e-4, score_tol=2e-4):
+    """The bench's own N-best of the utterances of its set that tests/golden/beam_nbest_fullsize.npz holds (decoded there
+    by the UNMODIFIED reference, tools/make_golden.py) against the reference's: identical 1-best, or a tie by the
+    REFERENCE's scores (the device 1-best is in the reference N-best within tie_tol of its best)."""
+    path = os.path.join(ROOT, "tests", "golden", "beam_nbest_fullsize.npz")
+    if not os.path.exists(path):
+        return None
+    g = np.load(path, allow_pickle=False)
+    out = {"identical": 0, "ties": 0, "different": 0, "n": 0, "max_score_diff": 0.0}
+    for c in range(int(g["n_cases"])):
+        u, n_frames = int(g["case%d_utt" % c]), int(g["case%d_len" % c])
+        if u >= tok.shape[0]:
+            continue                                   # a fixture outside the bench set (the short ones of the tests)
+        out["n"] += 1
+        m = int(ln[u, 0])
+        mine = tok[u, 0, :m].tolist()
+        ref = [(g["case%d_tok%d" % (c, j)].tolist(), float(g["case%d_avg%d" % (c, j)])) for j in range(int(g["case%d_nbest" % c]))]
+        if mine == ref[0][0]:
+            out["identical"] += 1
+            out["max_score_diff"] = max(out["max_score_diff"], abs(float(avg[u, 0]) - ref[0][1]))
+        elif any(mine == r[0] and abs(r[1] - ref[0][1]) < tie_tol for r in ref):
+            out["ties"] += 1
+        else:
+            out["different"] += 1
+    out["tie_tol"] = tie_tol
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
@@ -164,7 +205,7 @@ def run_b200(args):
     batches = shard.make_batches(shards[rank], lengths, args.max_utts, args.max_padded_frames)
     cap = int(np.ceil(lengths.max() * MAX_RATIO)) + 1
     rows = max(len(s) for s in shards)
-    rsize = shard.ragged_size(shards, lengths, BEAM, MAX_RATIO) if args.ragged_gather else 0
+    rsize = shard.ragged_size(shards, lengths, BEAM, MAX_RATIO)
 
     host = [make_features(b, lengths, pin=True) for b in batches]            # pinned host buffers
     resident = [(f.to(dev), l.to(dev)) for f, l in host]                      # HBM-resident copies
@@ -172,35 +213,38 @@ def run_b200(args):
     if args.ragged_h2d:                                                        # only the valid frames are copied
         h2d_bytes = sum(int(l.sum()) * f.shape[2] * 4 + l.numel() * 8 for f, l in host)
     in_bytes = sum(f.numel() * 4 for f, _ in resident)
+    # N-best of this rank's shard: packed ON THE DEVICE into the ragged gather buffer, all-gathered where it lies,
+    # read back once into pinned host memory (shard.RaggedPacker / gather_nbest)
+    packer = shard.RaggedPacker(shards[rank], lengths, BEAM, MAX_RATIO, rsize, dev)
+    dec.profile_phases = "coarse"
+    phase_ev = []
 
     def one_pass(from_host):
-        parts, ids = [], []
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
+        packer.reset()
         for b, hb, rb in zip(batches, host, resident):
             if from_host and args.ragged_h2d:
-                parts.append(dec.decode_batch_from_host(hb[0], hb[1], dev, return_arrays=True))   # valid frames only cross the bus
-                ids.extend(b)
-                continue
-            if from_host:
-                feat, fl = hb[0].to(dev, non_blocking=True), hb[1].to(dev, non_blocking=True)
+                part = dec.decode_batch_from_host(hb[0], hb[1], dev, return_arrays="device")   # valid frames only cross the bus
             else:
-                feat, fl = rb
-            parts.append(dec.decode_batch(feat, fl, return_arrays=True))      # N-best read back to the host
-            ids.extend(b)
-        width = max(p[0].shape[2] for p in parts)
-        pad = lambda a: torch.nn.functional.pad(a, (0, width - a.shape[2]))
-        tok = torch.cat([pad(p[0]) for p in parts]); sc = torch.cat([pad(p[1]) for p in parts])
-        ln = torch.cat([p[2] for p in parts]); avg = torch.cat([p[3] for p in parts]); n = torch.cat([p[4] for p in parts])
-        if args.ragged_gather:                                                # 4.5x fewer bytes through the gather (shard.py)
-            local_buf = shard.pack_nbest_ragged(ids, tok, sc, ln, avg, n, shards[rank], lengths, BEAM, MAX_RATIO, rsize)
-        else:
-            local_buf = shard.pack_nbest(ids, tok, sc, ln, avg, n, cap, rows)
-        full = shard.gather_nbest(local_buf, dev)                             # the one collective (no-op at N=1)
-        return local_buf, full
+                if from_host:
+                    feat, fl = hb[0].to(dev, non_blocking=True), hb[1].to(dev, non_blocking=True)
+                else:
+                    feat, fl = rb
+                part = dec.decode_batch(feat, fl, return_arrays="device")
+            ev[1].record()
+            packer.pack(b, *part)
+        ev[2].record()
+        full = shard.gather_nbest(packer.buf, marks=(ev[3], ev[4]))           # the one collective (no-op at N=1) + the read-back
+        phase_ev.append(ev)
+        return packer.buf, full
 
     def timed(from_host, steps, warmup):
         for _ in range(warmup):
             one_pass(from_host)
         dec.prefix_events = []
+        dec.phase_ms = {}
+        del phase_ev[:]
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -216,13 +260,21 @@ def run_b200(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        # per-phase device-clock time of a pass (CUDA events at the phase boundaries), max over ranks
+        names = ["encode", "ctc_posterior", "steps", "finalize", "pack", "gather", "d2h", "other"]
+        ph = dict(dec.phase_ms)
+        ph["pack"] = sum(e[1].elapsed_time(e[2]) for e in phase_ev)
+        ph["gather"] = sum(e[2].elapsed_time(e[3]) for e in phase_ev)
+        ph["d2h"] = sum(e[3].elapsed_time(e[4]) for e in phase_ev)
+        ph["other"] = e0.elapsed_time(e1) - sum(ph.get(k, 0.0) for k in names[:-1])      # feature copy, sort / index set-up, host gaps
+        vals = torch.tensor([e0.elapsed_time(e1)] + [ph.get(k, 0.0) / steps for k in names], device=dev, dtype=torch.float64)
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         clocks = sampler.stop() if rank == 0 else None
-        return float(ms.item()), ops.launch_count() - l0, clocks, local_buf, full
+        phases = {k: round(float(v), 3) for k, v in zip(names, vals[1:].tolist())}
+        return float(vals[0].item()), ops.launch_count() - l0, clocks, local_buf, full, phases
 
-    ms, launches, clocks, local_buf, full = timed(False, args.steps, args.warmup)
+    ms, launches, clocks, local_buf, full, phases = timed(False, args.steps, args.warmup)
     # prefix-score kernel: per-launch CUDA-event durations collected inside the timed region
     ev = dec.prefix_events
     k_ms = [a.elapsed_time(b) for a, b, _, _ in ev]
@@ -238,8 +290,34 @@ def run_b200(args):
     achieved_rows = units_rows * bytes_per_unit / (k_total_ms * 1e-3) / 1e9 if k_total_ms > 0 else 0.0
     dec.profile_prefix = False
 
-    e2e_ms, _, _, _, _ = timed(True, args.steps, 1)
+    e2e_ms, _, _, _, _, e2e_phases = timed(True, args.steps, 1)
     stats_units = units_formula / max(1, args.steps)
+
+    # ---- result checks, outside the timed regions ----------------------------------------------------------------
+    try:
+        tok, sc, ln, avg, nn = shard.unpack_nbest_ragged(full, shards, lengths, BEAM, MAX_RATIO, rsize)
+        ok = True
+    except AssertionError:
+        ok = False
+    parity = golden_parity(tok, sc, ln, avg, nn) if (ok and rank == 0 and args.n_utts == N_UTTS) else None
+    sharded_equal = None
+    if world > 1 and ok:
+        # N-GPU == 1-GPU: rank 0 decodes the LAST rank's shard itself (same batches) and compares with what the gather
+        # delivered for those utterances, bit for bit
+        if rank == 0:
+            other = world - 1
+            o_batches = shard.make_batches(shards[other], lengths, args.max_utts, args.max_padded_frames)
+            sharded_equal = True
+            for ob in o_batches:
+                f, l = make_features(ob, lengths, pin=False)
+                t2, s2, l2, a2, n2 = dec.decode_batch(f.to(dev), l.to(dev), return_arrays=True)
+                idx = torch.as_tensor(np.asarray(ob, dtype=np.int64))
+                w = t2.shape[2]
+                same = (torch.equal(tok[idx][:, :, :w], t2) and torch.equal(ln[idx], l2) and torch.equal(nn[idx], n2)
+                        and torch.equal(sc[idx][:, :, :w].contiguous().view(torch.int32), s2.contiguous().view(torch.int32))
+                        and torch.equal(avg[idx].contiguous().view(torch.int32), a2.contiguous().view(torch.int32)))
+                sharded_equal = sharded_equal and bool(same)
+        dist.barrier()
 
     if rank != 0:
         # every rank leaves through the same barrier as rank 0 (a rank that returned early left rank 0 waiting
@@ -247,14 +325,6 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
         return
-    if args.ragged_gather:
-        try:
-            shard.unpack_nbest_ragged(full, shards, lengths, BEAM, MAX_RATIO, rsize)
-            ok = True
-        except AssertionError:
-            ok = False
-    else:
-        ok = int((full[:, 0] >= 0).sum()) == n_total
     line = {
         "metric": METRIC, "value": n_total * args.steps / (ms * 1e-3), "unit": "utts/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -266,9 +336,9 @@ def run_b200(args):
                    "h2d": "valid frames only, one copy per utterance" if args.ragged_h2d else "padded [U,Lmax,D] tensor, one copy",
                    "lm_gemm_operands": dec.lm_split, "vgg_gemm_operands": dec.vgg_split,
                    "l2": "inputs (%.1f GB features + GB-scale prefix states per batch) exceed the 126 MB L2; no flush needed" % (in_bytes / 1e9),
-                   "parallelism": "utterance shards x%d, one all-gather of N-best%s" % (world, " (ragged buffer)" if args.ragged_gather else "")},
+                   "parallelism": "utterance shards x%d, one all-gather of the ragged N-best buffer (packed on the device, one pinned read-back)" % world},
         "e2e": {"value": n_total * args.steps / (e2e_ms * 1e-3), "unit": "utts/s",
-                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(local_buf.numel() * 4)},
+                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(full.numel() * 4), "phases_ms": e2e_phases},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "prefix_score_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -280,7 +350,8 @@ def run_b200(args):
                      "kernel_share_of_step": k_total_ms / ms,
                      "achieved_computed_rows_only": achieved_rows, "frac_computed_rows_only": achieved_rows / peak,
                      "cand_frames_per_s": units_formula / (k_total_ms * 1e-3) if k_total_ms > 0 else 0.0},
-        "nbest_complete": bool(ok),
+        "phases_ms": phases,
+        "nbest_complete": bool(ok), "nbest_parity": parity, "sharded_equals_single": sharded_equal,
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args, sample_utts=args.cpu_sample)
@@ -452,7 +523,7 @@ def main():
                     help="log-add-exp evaluator of the prefix-score kernel (default: the decoder's, lut)")
     ap.add_argument("--ragged-h2d", action="store_true",
                     help="e2e leg: copy only the valid frames of every utterance (BeamDecoder.decode_batch_from_host)")
-    ap.add_argument("--ragged-gather", action="store_true", help="gather the ragged N-best buffer (shard.pack_nbest_ragged)")
+    ap.add_argument("--ragged-gather", action="store_true", help="(default now; kept for old command lines)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0)

@@ -194,7 +194,8 @@ class BeamDecoder(nn.Module):
     def decode_batch(self, audio_feature, feature_len, return_arrays=False):
         """audio_feature [U,Lmax,D] (zero padded), feature_len [U] -> list (per utterance) of
         N-best ``Hypothesis`` lists, best first.  ``return_arrays=True`` returns the raw
-        (tokens, scores, lens, avg, n) CPU tensors instead (used by the sharded driver)."""
+        (tokens, scores, lens, avg, n) CPU tensors instead, ``return_arrays="device"`` the same as CUDA tensors
+        (no read-back: the sharded driver packs and gathers them on the device)."""
         if not audio_feature.is_cuda:
             raise L.E2EError("BeamDecoder has no CPU path: move the features and the decoder to a CUDA device")
         # the hand-written kernels are enqueued on the CURRENT device's current stream: make the features' device current
@@ -227,14 +228,16 @@ class BeamDecoder(nn.Module):
 
         marks = []
 
-        def mark(name):
-            if self.profile_phases:
+        coarse = self.profile_phases == "coarse"        # phase boundaries only: nothing is recorded inside the step loop
+
+        def mark(name, boundary=False):
+            if self.profile_phases and (boundary or not coarse):
                 e = torch.cuda.Event(enable_timing=True)
                 e.record()
                 marks.append((name, e))
 
         with _Fp32Math():
-            mark("start")
+            mark("start", True)
             knobs = (self.split_gemm, self.fused_attention, self.lm_split, self.vgg_split)
             if self._stepper is None or self._stepper[0] != dev or self._stepper[1] != knobs:
                 self._stepper = (dev, knobs, BatchedStepper(self.asr, self.lm if self.apply_lm else None,
@@ -242,7 +245,7 @@ class BeamDecoder(nn.Module):
             stepper = self._stepper[2]
             stepper.mark = mark
             enc, enc_len = stepper.encode(audio_feature, feature_len.to(dev))
-            mark("encode")
+            mark("encode", True)
             enc_len32 = enc_len.to(torch.int32).contiguous()
             stepper.start(enc, enc_len, beam)
             t_max = enc.shape[1]
@@ -263,7 +266,7 @@ class BeamDecoder(nn.Module):
             if self.profile_prefix and self.apply_ctc:
                 t_np, s_np = enc_len.cpu().numpy().astype(np.int64), max_len.numpy().astype(np.int64)
 
-            mark("ctc_posterior")
+            mark("ctc_posterior", True)
             for step in range(n_steps):                                            # decode.py:104
                 k = n_run[step]
                 att_logits, lm_logits = stepper.step(buf.last_tok64[:k].view(-1), k)
@@ -296,24 +299,28 @@ class BeamDecoder(nn.Module):
                 stepper.reorder(buf.parent_row)
                 mark("reorder")
 
+            mark("steps", True)
             tok, sc, ln, avg, n = ops.beam_finalize(buf)
-            mark("finalize")
+            mark("finalize", True)
             status = buf.status.cpu()
             inv = torch.as_tensor(inverse, device=dev)
             # N-best back to the host through pinned buffers (the caching host allocator reuses them)
             dev_out = [a.index_select(0, inv) for a in (tok, sc, ln, avg, n)]
-            host_out = [torch.empty(a.shape, dtype=a.dtype, pin_memory=True) for a in dev_out]
-            for h, a in zip(host_out, dev_out):
-                h.copy_(a, non_blocking=True)
-            torch.cuda.current_stream(dev).synchronize()
-            tok, sc, ln, avg, n = host_out
+            if return_arrays == "device":
+                tok, sc, ln, avg, n = dev_out              # stays on the device (shard.RaggedPacker packs it there)
+            else:
+                host_out = [torch.empty(a.shape, dtype=a.dtype, pin_memory=True) for a in dev_out]
+                for h, a in zip(host_out, dev_out):
+                    h.copy_(a, non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+                tok, sc, ln, avg, n = host_out
             status = status[torch.as_tensor(inverse)]
 
         if self.profile_phases:
             torch.cuda.synchronize()
             for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
                 self.phase_ms[name] = self.phase_ms.get(name, 0.0) + a.elapsed_time(b)
-        self._raise_like_reference(status, n, max_len)
+        self._raise_like_reference(status, None, max_len)
         enc_len_cpu = enc_len.cpu()[torch.as_tensor(inverse)]
         max_len = max_len[torch.as_tensor(inverse)]
         self.last_stats = {

@@ -271,7 +271,7 @@ def ragged_size(shards, lengths, beam, max_len_ratio):
     return max([ragged_layout(ids, lengths, beam, max_len_ratio)[1] for ids in shards] + [1])
 
 
-def gather_nbest(local_buf, device=None):
+def gather_nbest(local_buf, device=None, marks=None):
     """The one collective of the sharded decode: all-gather of the packed buffers (same shape on every rank).
     Returns the concatenation of all ranks' buffers on the host.  A CUDA ``local_buf`` (RaggedPacker) is gathered where
     it lies and read back ONCE into pinned host memory; a CPU buffer (gloo tests, legacy CPU packing) is sent as it is."""
@@ -282,8 +282,12 @@ def gather_nbest(local_buf, device=None):
             recv = torch.empty((dist.get_world_size() * local_buf.shape[0],) + tuple(local_buf.shape[1:]),
                                dtype=local_buf.dtype, device=local_buf.device)
             dist.all_gather_into_tensor(recv, local_buf.contiguous())
+        if marks is not None:
+            marks[0].record()                                                  # (CUDA events: after the gather, after the read-back)
         host = torch.empty(recv.shape, dtype=recv.dtype, pin_memory=True)     # the caching host allocator reuses the block
         host.copy_(recv, non_blocking=True)
+        if marks is not None:
+            marks[1].record()
         torch.cuda.current_stream(local_buf.device).synchronize()
         return host
     if not multi:

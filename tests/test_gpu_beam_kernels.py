@@ -192,6 +192,7 @@ def test_beam_combine_prune_hand_made_states(cuda, case):
         att[2, 1] = att[2].max() + 4.0
     elif case == "eos_boundary_not_closed":
         # <eos> is in the top-k but log p(eos) <= 1.5 * log p(best other): it stays an ordinary token (src/decode.py:235-248)
+        parents = parents[:1]                             # one live parent: all of its top-k children survive the prune
         att[0] = torch.from_numpy(rng.standard_normal(vocab).astype(np.float32) * 0.1 - 10.0)
         att[0, 7], att[0, 1] = 5.0, 1.0
     elif case == "min_len_blocks":

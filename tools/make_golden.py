@@ -11,7 +11,8 @@
 
 * ``beam_nbest_fullsize.npz`` — the same for the FULL-SIZE bench models (synth.ASR_MODEL_CFG: librispeech_asr.yaml dims
   with the VGG front end, 19 M parameters; 4x1024 RNNLM; output layers unscaled, exactly what bench.py builds) at the
-  bench's decode settings (beam 8, ctc 0.5, lm 0.5, ratios 0.01 / 0.2) on a few short utterances.
+  bench's decode settings (beam 8, ctc 0.5, lm 0.5, ratios 0.01 / 0.2) on five short utterances and on 16 utterances of the
+  bench's own 2620-utterance set at the quantile midpoints of its length distribution (bench.py checks its N-best of these).
 
 The reference cannot travel to the GPU box, these vectors can.
 """
@@ -106,34 +107,60 @@ def beam_nbest(ref):
     print("beam_nbest_tiny.npz: %d cases" % n_case)
 
 
-FULLSIZE_CASES = [(900001, 152), (900002, 240), (900003, 320), (900004, 480), (900005, 640)]      # (utterance id, input frames)
+FULLSIZE_SHORT = [(900001, 152), (900002, 240), (900003, 320), (900004, 480), (900005, 640)]      # (utterance id, input frames)
 
 
-def beam_nbest_fullsize(ref):
-    vocab, beam, lm_w, ctc_w = 31, 8, 0.5, 0.5
-    mine = synth.build_asr(vocab, seed=0)
-    rasr = ref.ASR(synth.FEAT_DIM, vocab, True, **copy.deepcopy(synth.ASR_MODEL_CFG)).eval()
-    rasr.load_state_dict(mine.state_dict())
-    lm = synth.build_lm(vocab, seed=1)
-    tmp = tempfile.mkdtemp()
-    torch.save({"model": lm.state_dict()}, os.path.join(tmp, "lm.pth"))
-    yaml.safe_dump({"model": synth.LM_MODEL_CFG}, open(os.path.join(tmp, "lm.yaml"), "w"))
-    dec = ref.BeamDecoder(rasr, None, beam, 0.01, 0.2, lm_path=os.path.join(tmp, "lm.pth"),
-                          lm_config=os.path.join(tmp, "lm.yaml"), lm_weight=lm_w, ctc_weight=ctc_w)
-    out = {"beam": np.int32(beam), "lm_w": np.float32(lm_w), "ctc_w": np.float32(ctc_w), "n_cases": np.int32(len(FULLSIZE_CASES))}
-    for k, (utt, n) in enumerate(FULLSIZE_CASES):
-        with torch.no_grad():
-            hyps = dec(synth.utterance(utt, n)[None], torch.LongTensor([n]))
+def fullsize_cases(n_set=16):
+    """The five short fixtures + ``n_set`` utterances OF THE BENCH'S OWN SET (cfg2: 2620 dev-clean-like lengths, seed 2) at the
+    quantile midpoints of its length distribution — bench.py compares its N-best of exactly these utterances."""
+    lengths = synth.devclean_lengths(2620, seed=2)
+    order = np.argsort(lengths, kind="stable")
+    pos = ((np.arange(n_set) + 0.5) / n_set * len(order)).astype(np.int64)
+    return FULLSIZE_SHORT + [(int(order[p]), int(lengths[order[p]])) for p in pos]
+
+
+_FS = {}
+
+
+def _fullsize_worker(job):
+    k, utt, n = job
+    torch.set_num_threads(1)
+    if "dec" not in _FS:
+        ref = refload.load()
+        vocab, beam, lm_w, ctc_w = 31, 8, 0.5, 0.5
+        mine = synth.build_asr(vocab, seed=0)
+        rasr = ref.ASR(synth.FEAT_DIM, vocab, True, **copy.deepcopy(synth.ASR_MODEL_CFG)).eval()
+        rasr.load_state_dict(mine.state_dict())
+        lm = synth.build_lm(vocab, seed=1)
+        tmp = tempfile.mkdtemp()
+        torch.save({"model": lm.state_dict()}, os.path.join(tmp, "lm.pth"))
+        yaml.safe_dump({"model": synth.LM_MODEL_CFG}, open(os.path.join(tmp, "lm.yaml"), "w"))
+        _FS["dec"] = ref.BeamDecoder(rasr, None, beam, 0.01, 0.2, lm_path=os.path.join(tmp, "lm.pth"),
+                                     lm_config=os.path.join(tmp, "lm.yaml"), lm_weight=lm_w, ctc_weight=ctc_w)
+    with torch.no_grad():
+        hyps = _FS["dec"](synth.utterance(utt, n)[None], torch.LongTensor([n]))
+    return k, [(np.array(h.outIndex, np.int32), np.array([float(s) for s in h.output_scores], np.float32),
+                np.float32(float(h.avgScore()))) for h in hyps]
+
+
+def beam_nbest_fullsize(ref, procs=8):
+    """One utterance per worker process, the reference BeamDecoder with one torch thread each (longest first)."""
+    import multiprocessing as mp
+    cases = fullsize_cases()
+    jobs = sorted([(k, utt, n) for k, (utt, n) in enumerate(cases)], key=lambda j: -j[2])
+    with mp.get_context("fork").Pool(procs) as pool:
+        res = dict(pool.imap_unordered(_fullsize_worker, jobs))
+    out = {"beam": np.int32(8), "lm_w": np.float32(0.5), "ctc_w": np.float32(0.5), "n_cases": np.int32(len(cases))}
+    for k, (utt, n) in enumerate(cases):
+        hyps = res[k]
         key = "case%d" % k
         out[key + "_utt"], out[key + "_len"], out[key + "_nbest"] = np.int32(utt), np.int32(n), np.int32(len(hyps))
-        for j, h in enumerate(hyps):
-            out["%s_tok%d" % (key, j)] = np.array(h.outIndex, np.int32)
-            out["%s_sc%d" % (key, j)] = np.array([float(s) for s in h.output_scores], np.float32)
-            out["%s_avg%d" % (key, j)] = np.float32(float(h.avgScore()))
-        print("  full-size case %d: %d frames, %d tokens, best mean score %.6f, runner-up gap %.3g"
-              % (k, n, len(hyps[0].outIndex), float(hyps[0].avgScore()), float(hyps[0].avgScore()) - float(hyps[1].avgScore())), flush=True)
+        for j, (tok, sc, avg) in enumerate(hyps):
+            out["%s_tok%d" % (key, j)], out["%s_sc%d" % (key, j)], out["%s_avg%d" % (key, j)] = tok, sc, avg
+        print("  full-size case %d: utt %d, %d frames, %d tokens, best mean score %.6f, runner-up gap %.3g"
+              % (k, utt, n, len(hyps[0][0]), float(hyps[0][2]), float(hyps[0][2]) - float(hyps[1][2])), flush=True)
     np.savez_compressed(os.path.join(OUT, "beam_nbest_fullsize.npz"), **out)
-    print("beam_nbest_fullsize.npz: %d cases" % len(FULLSIZE_CASES))
+    print("beam_nbest_fullsize.npz: %d cases" % len(cases))
 
 
 if __name__ == "__main__":
@@ -141,7 +168,6 @@ if __name__ == "__main__":
     ref = refload.load()
     torch.set_num_threads(4)
     if len(sys.argv) > 1 and sys.argv[1] == "fullsize":      # leaves the other fixtures untouched
-        torch.set_num_threads(8)
         beam_nbest_fullsize(ref)
     else:
         prefix_chains(ref)
