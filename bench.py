@@ -153,7 +153,7 @@ def golden_parity(tok, sc, ln, avg, nn, tie_tol=5e-4, score_tol=2e-4):
     if not os.path.exists(path):
         return None
     g = np.load(path, allow_pickle=False)
-    out = {"identical": 0, "ties": 0, "different": 0, "n": 0, "max_score_diff": 0.0}
+    out = {"identical": 0, "ties": 0, "not_in_reference_nbest": 0, "n": 0, "max_score_diff": 0.0}
     for c in range(int(g["n_cases"])):
         u, n_frames = int(g["case%d_utt" % c]), int(g["case%d_len" % c])
         if u >= tok.shape[0]:
@@ -168,8 +168,8 @@ def golden_parity(tok, sc, ln, avg, nn, tie_tol=5e-4, score_tol=2e-4):
         elif any(mine == r[0] and abs(r[1] - ref[0][1]) < tie_tol for r in ref):
             out["ties"] += 1
         else:
-            out["different"] += 1
-    out["tie_tol"] = tie_tol
+            out["not_in_reference_nbest"] += 1         # the search paths diverged early (runner-up gaps of this random-init workload are
+    out["tie_tol"] = tie_tol                            # 1e-5 .. 7e-4); tests/test_gpu_fullsize_golden.py audits these by rescoring
     return out
 
 

@@ -71,6 +71,83 @@ ctc_log_softmax_kernel(const float *__restrict__ logits, int U, int Tmax, int V,
     }
 }
 
+// Large vocabularies (Vp > 128, e.g. the 10k subword vocabulary of BASELINE cfg3): one CTA per output row.  The row is
+// read from HBM ONCE with 16-byte loads into shared memory (ReLU applied on the way), max and sum-exp are block
+// reductions over the staged copy, and the log-probabilities leave as 16-byte stores: 8*V bytes of traffic per
+// frame-row, the algorithmic minimum, instead of three scalar passes over the row.
+constexpr int kWideThreads = 256;
+
+__global__ void __launch_bounds__(kWideThreads)
+ctc_log_softmax_wide_kernel(const float *__restrict__ logits, int U, int Tmax, int V, const int *__restrict__ enc_len,
+                            int apply_relu, float *__restrict__ x, int Vp)
+{
+    extern __shared__ __align__(16) float s_row[];        // [Vp]
+    __shared__ float s_red[kWideThreads / 32];
+    __shared__ float s_bcast;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long row = blockIdx.x;                      // = t*U + u
+    const int t = (int)(row / U), u = (int)(row % U);
+    float4 *__restrict__ out = reinterpret_cast<float4 *>(x + row * Vp);
+    const int groups = Vp >> 2;
+    const int tu = enc_len ? enc_len[u] : Tmax;
+    if (t >= tu) {
+        const float4 z = make_float4(E2E_CTC_LOGZERO, E2E_CTC_LOGZERO, E2E_CTC_LOGZERO, E2E_CTC_LOGZERO);
+        for (int g = tid; g < groups; g += kWideThreads) out[g] = z;
+        return;
+    }
+    const float *__restrict__ in = logits + ((long long)u * Tmax + t) * V;
+    const bool vec = ((V & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+    float m = -INFINITY;
+    if (vec) {
+        const float4 *in4 = reinterpret_cast<const float4 *>(in);
+        for (int g = tid; g < (V >> 2); g += kWideThreads) {
+            float4 a = __ldg(in4 + g);
+            if (apply_relu) { a.x = fmaxf(a.x, 0.0f); a.y = fmaxf(a.y, 0.0f); a.z = fmaxf(a.z, 0.0f); a.w = fmaxf(a.w, 0.0f); }
+            reinterpret_cast<float4 *>(s_row)[g] = a;
+            m = fmaxf(fmaxf(m, fmaxf(a.x, a.y)), fmaxf(a.z, a.w));
+        }
+    } else {
+        for (int v = tid; v < V; v += kWideThreads) {
+            float a = __ldg(in + v);
+            if (apply_relu) a = fmaxf(a, 0.0f);
+            s_row[v] = a;
+            m = fmaxf(m, a);
+        }
+    }
+    m = warp_max(m);
+    if (lane == 0) s_red[wid] = m;
+    __syncthreads();
+    if (tid == 0) {
+        float mm = s_red[0];
+        for (int w = 1; w < kWideThreads / 32; ++w) mm = fmaxf(mm, s_red[w]);
+        s_bcast = mm;
+    }
+    __syncthreads();
+    m = s_bcast;
+    float sum = 0.0f;
+    for (int v = tid; v < V; v += kWideThreads) sum += expf(s_row[v] - m);
+    sum = warp_sum(sum);
+    __syncthreads();                                       // s_red / s_bcast are reused
+    if (lane == 0) s_red[wid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        float ss = 0.0f;
+        for (int w = 0; w < kWideThreads / 32; ++w) ss += s_red[w];
+        s_bcast = logf(ss);
+    }
+    __syncthreads();
+    const float ls = s_bcast;
+    for (int g = tid; g < groups; g += kWideThreads) {
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int v = g * 4 + k;
+            o[k] = (v < V) ? (s_row[v] - m) - ls : E2E_CTC_LOGZERO;
+        }
+        out[g] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // One thread per utterance: the reference's running sum is sequential fp32 (src/ctc.py:24-26),
 // so the adds are kept in that order.  r0: [U][Tmax][1][2].
 __global__ void ctc_init_state_kernel(const float *__restrict__ x, int Tmax, int U, int Vp,
@@ -101,7 +178,14 @@ extern "C" int e2e_ctc_log_softmax(const float *logits, int U, int Tmax, int V, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (Vp <= 128)
         ctc_log_softmax_kernel<true><<<blocks, kRowWarps * 32, 0, st>>>(logits, U, Tmax, V, enc_len, apply_relu, x, Vp);
-    else
+    else if ((size_t)Vp * 4 <= 160 * 1024 && rows <= 0x7fffffffLL) {
+        const size_t smem = (size_t)Vp * 4;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(ctc_log_softmax_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return set_error(E2E_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        }
+        ctc_log_softmax_wide_kernel<<<(unsigned)rows, kWideThreads, smem, st>>>(logits, U, Tmax, V, enc_len, apply_relu, x, Vp);
+    } else
         ctc_log_softmax_kernel<false><<<blocks, kRowWarps * 32, 0, st>>>(logits, U, Tmax, V, enc_len, apply_relu, x, Vp);
     count_launch();
     return check_launch("e2e_ctc_log_softmax");

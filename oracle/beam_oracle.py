@@ -117,12 +117,17 @@ def prune(pool, beam_size):
 
 
 def decode_utterance(asr, feat, feat_len, beam_size, min_len_ratio, max_len_ratio,
-                     lm=None, lm_weight=0.0, ctc_weight=0.0, trace=None, scorer_cls=None):
+                     lm=None, lm_weight=0.0, ctc_weight=0.0, trace=None, scorer_cls=None, force=None):
     """Joint CTC/attention(+LM) beam search of ONE utterance on CPU.
 
     feat [1, L, D] float, feat_len [1] long.  Returns the N-best list of Beam
     objects, best first (decode.py:183).  ``trace`` (a list) receives one dict per
     (step, parent) with the tensors the device kernels are checked against.
+
+    ``force`` (token ids): RESCORING for the tie audit — the search keeps one hypothesis and is made
+    to follow these tokens, every score computed by exactly the operations above (candidate pre-prune with
+    ``beam_size``'s candidate count, CTC blend, LM add, <eos> threshold); returns [that hypothesis].  A token outside
+    the CTC candidates raises the reference's ValueError (decode.py:252): the reference could not have produced it.
     """
     assert feat.shape[0] == 1, "Batchsize == 1 is required for beam search"
     assert asr.enable_att
@@ -149,7 +154,7 @@ def decode_utterance(asr, feat, feat_len, beam_size, min_len_ratio, max_len_rati
 
     live = [Beam([], [], dec_state0, None, None, state0, 0)]
     done, stats = [], {"cand_frames": 0, "steps": max_steps, "enc_frames": int(enc.shape[1])}
-    for step in range(max_steps):
+    for step in range(max_steps if force is None else len(force)):
         pool = []
         for hyp in live:
             tok_prev = hyp.tokens[-1] if hyp.tokens else 0
@@ -186,7 +191,11 @@ def decode_utterance(asr, feat, feat_len, beam_size, min_len_ratio, max_len_rati
                 if rec is not None:
                     rec["lm_logits"] = lm_out.detach().clone()
 
-            top_vals, top_ids = score.squeeze(0).topk(beam_size)
+            if force is None:
+                top_vals, top_ids = score.squeeze(0).topk(beam_size)
+            else:
+                top_ids = torch.LongTensor([int(force[step])]).to(device)
+                top_vals = score.squeeze(0)[top_ids]
             att_map = asr.attention.att_layer.prev_att.cpu() if keep_att else None
             if rec is not None:
                 rec.update(top_ids=top_ids.clone(), top_vals=top_vals.clone(), att_logp=att_logp.detach().clone())
@@ -198,8 +207,12 @@ def decode_utterance(asr, feat, feat_len, beam_size, min_len_ratio, max_len_rati
                 if beam_size == 1:
                     return done
             pool.extend(children)
+            if force is not None and closed is not None:
+                return [closed]
         live = prune(pool, beam_size)
 
+    if force is not None:
+        return live
     done += live
     done.sort(key=lambda b: b.mean_score(), reverse=True)
     result = done[:beam_size]

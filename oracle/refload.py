@@ -103,10 +103,13 @@ class _Null:
         return False
 
 
-def load_test_asr(staged=None):
-    """The reference's ``bin.test_asr`` module (for ``beam_decode``, bin/test_asr.py:159-173)."""
+def load_test_asr(staged=None, fresh=False):
+    """The reference's ``bin.test_asr`` module (for ``beam_decode``, bin/test_asr.py:159-173).  ``fresh``: import it
+    again even if it already is (its ``from src.decode import BeamDecoder`` binds at import time)."""
     kind, root = _root(staged)
     load(staged)
+    if fresh:
+        sys.modules.pop("bin.test_asr", None)
     added = []
     for name, attrs in (("src.solver", {"BaseSolver": object}), ("src.data", {"load_dataset": None, "load_wav_dataset": None})):
         if name not in sys.modules:
