@@ -57,8 +57,6 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "e2e_attention_loc_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
-                                       c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "e2e_attention_loc_full": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_float, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_void_p, c_void_p, c_void_p]),

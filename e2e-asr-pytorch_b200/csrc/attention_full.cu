@@ -180,17 +180,9 @@ attention_energy_kernel(const AttFullParams p)
 }
 
 // kernel B: masked softmax + context for beam slots [b_lo, b_hi) of one utterance
-// kStaged (opt-in, E2E_AF_CTX_STAGED=1; E % 4 == 0, E <= 4 * kAfThreads): the value rows reach the context product through
-// shared memory — tiles of kCtxTile consecutive rows (one contiguous block of the [T][E] matrix) brought in by the
-// bulk-copy engine, two stages, completion on an mbarrier — so the bytes in flight per SM no longer depend on how many
-// loads a thread can hold in registers.  Accumulation order, hence the result, is the same as in the direct variant.
-constexpr int kCtxTile = 16;
-
-template <bool kStaged>
 __global__ void __launch_bounds__(kAfThreads)
 attention_softmax_context_kernel(const AttFullParams p)
 {
-    extern __shared__ __align__(128) unsigned char ctx_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int u = blockIdx.x / p.slot_ctas, part = blockIdx.x - u * p.slot_ctas;
     const int T = p.T, B = p.B;
@@ -222,92 +214,7 @@ attention_softmax_context_kernel(const AttFullParams p)
     const float *vbase = p.value + (size_t)u * T * p.E;
     constexpr int kBC = 8;
     const bool t_vec = (T & 3) == 0;
-    if constexpr (kStaged) {
-        const int E = p.E;
-        float *vt = reinterpret_cast<float *>(ctx_smem);                         // [2][kCtxTile][E]
-        uint64_t *bars = reinterpret_cast<uint64_t *>(ctx_smem + (size_t)2 * kCtxTile * E * 4);
-        if (tid == 0) {
-            mbar_init(&bars[0], 1);
-            mbar_init(&bars[1], 1);
-            mbar_fence_init();
-        }
-        __syncthreads();
-        const int n_tiles = (Tu + kCtxTile - 1) / kCtxTile;
-        auto issue = [&](int use, int k) {       // thread 0: tile k of the utterance into stage use & 1
-            const int t0 = k * kCtxTile;
-            const uint32_t bytes = (uint32_t)min(kCtxTile, Tu - t0) * (uint32_t)E * 4u;
-            uint64_t *bar = &bars[use & 1];
-            mbar_arrive_expect_tx(bar, bytes);
-            bulk_g2s(vt + (size_t)(use & 1) * kCtxTile * E, vbase + (size_t)t0 * E, bytes, bar);
-        };
-        const int e = tid * 4;
-        int use0 = 0;                            // tiles consumed so far (stage = use & 1, mbarrier phase = (use >> 1) & 1)
-        for (int bc = b_lo; bc < b_hi; bc += kBC) {
-            const int nb = min(kBC, b_hi - bc);
-            const float *ar = arow + (size_t)bc * T;
-            float acc[kBC][4];
-#pragma unroll
-            for (int b = 0; b < kBC; ++b)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[b][i] = 0.0f;
-            if (tid == 0 && n_tiles > 0) {
-                issue(use0, 0);
-                if (n_tiles > 1) issue(use0 + 1, 1);
-            }
-            for (int k = 0; k < n_tiles; ++k) {
-                const int use = use0 + k;
-                mbar_wait(&bars[use & 1], (uint32_t)(use >> 1) & 1u);
-                const int t0 = k * kCtxTile, rows = min(kCtxTile, Tu - t0);
-                if (e < E) {
-                    const float *vs = vt + (size_t)(use & 1) * kCtxTile * E + e;
-                    int tt = 0;
-                    for (; tt + 4 <= rows; tt += 4) {
-                        float4 v[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) v[q] = *reinterpret_cast<const float4 *>(vs + (size_t)(tt + q) * E);
-#pragma unroll
-                        for (int b = 0; b < kBC; ++b) {
-                            if (b < nb) {
-                                float a[4];
-                                if (t_vec) {
-                                    const float4 a4 = *reinterpret_cast<const float4 *>(ar + (size_t)b * T + t0 + tt);
-                                    a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
-                                } else {
-#pragma unroll
-                                    for (int q = 0; q < 4; ++q) a[q] = ar[(size_t)b * T + t0 + tt + q];
-                                }
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    acc[b][0] = fmaf(a[q], v[q].x, acc[b][0]); acc[b][1] = fmaf(a[q], v[q].y, acc[b][1]);
-                                    acc[b][2] = fmaf(a[q], v[q].z, acc[b][2]); acc[b][3] = fmaf(a[q], v[q].w, acc[b][3]);
-                                }
-                            }
-                        }
-                    }
-                    for (; tt < rows; ++tt) {
-                        const float4 v = *reinterpret_cast<const float4 *>(vs + (size_t)tt * E);
-#pragma unroll
-                        for (int b = 0; b < kBC; ++b) {
-                            if (b < nb) {
-                                const float a = ar[(size_t)b * T + t0 + tt];
-                                acc[b][0] = fmaf(a, v.x, acc[b][0]); acc[b][1] = fmaf(a, v.y, acc[b][1]);
-                                acc[b][2] = fmaf(a, v.z, acc[b][2]); acc[b][3] = fmaf(a, v.w, acc[b][3]);
-                            }
-                        }
-                    }
-                }
-                __syncthreads();                                          // every thread is done with this stage
-                if (tid == 0 && k + 2 < n_tiles) issue(use + 2, k + 2);  // ... so it can be refilled
-            }
-            use0 += n_tiles;
-            if (e < E) {
-#pragma unroll
-                for (int b = 0; b < kBC; ++b)
-                    if (b < nb)
-                        *reinterpret_cast<float4 *>(p.ctx + ((size_t)u * B + bc + b) * E + e) = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
-            }
-        }
-    } else {
+    {
         for (int bc = b_lo; bc < b_hi; bc += kBC) {
             const int nb = min(kBC, b_hi - bc);
             const float *ar = arow + (size_t)bc * T;
@@ -417,17 +324,7 @@ static int att_full_launch(AttFullParams &p, int KP, int n_run, cudaStream_t st)
     p.unit_ctas = ua;
     p.slot_ctas = ub;
     kern<<<(unsigned)(n_run * ua), kAfThreads, smem, st>>>(p);
-    static const bool staged_env = []() { const char *e = getenv("E2E_AF_CTX_STAGED"); return e && atoi(e) != 0; }();
-    if (staged_env && (p.E & 3) == 0 && p.E <= 4 * kAfThreads) {
-        const size_t smem_b = (size_t)2 * kCtxTile * p.E * 4 + 16;
-        if (smem_b > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(attention_softmax_context_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
-            if (e != cudaSuccess) return set_error(E2E_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        }
-        attention_softmax_context_kernel<true><<<(unsigned)(n_run * ub), kAfThreads, smem_b, st>>>(p);
-    } else {
-        attention_softmax_context_kernel<false><<<(unsigned)(n_run * ub), kAfThreads, 0, st>>>(p);
-    }
+    attention_softmax_context_kernel<<<(unsigned)(n_run * ub), kAfThreads, 0, st>>>(p);
     count_launch(2);
     return check_launch("e2e_attention_loc_full");
 }

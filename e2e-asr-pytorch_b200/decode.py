@@ -138,7 +138,7 @@ class BeamDecoder(nn.Module):
         # the same choice for the VGG convolutions (their activations have no fixed range: the scale is chosen on
         # the device from the running maximum of every layer's input, csrc/conv_split.cu)
         self.vgg_split = os.environ.get("E2E_VGG_SPLIT", "bf16x3")
-        self.fused_attention = True     # hand-written location-aware attention kernel (csrc/attention_step.cu)
+        self.fused_attention = True     # hand-written location-aware attention kernel (csrc/attention_full.cu)
         self._stepper = None            # (device, split_gemm, stepper): weights are split once per device
         self.profile_prefix = False     # bench.py: CUDA-event pair around every prefix-score launch
         self.prefix_events = []         # (start, end, cand_frames [SURVEY §8d formula], cand_frames actually computed)

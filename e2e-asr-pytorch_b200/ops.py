@@ -212,22 +212,6 @@ def nbest_pack_ragged(tok, sc, ln, avg, n, slot, tok_off, cap, hdr, tok_out, sc_
                                           L.ptr(tok_off), L.ptr(cap), L.ptr(hdr), L.ptr(tok_out), L.ptr(sc_out), _stream()))
 
 
-def attention_loc_step(key, query, loc_feat, enc_len, w_proj, w_energy, b_energy, temperature, beam, out=None):
-    """Fused location-aware attention energies + masked softmax: key [U,T,A], query [n,A],
-    loc_feat [n,K,T] (conv of the previous alignment) -> attn [n,T]."""
-    for t, nm in ((key, "key"), (query, "query"), (loc_feat, "loc_feat"), (w_proj, "w_proj"), (w_energy, "w_energy")):
-        _chk(t, F32, nm)
-    _chk(enc_len, I32, "enc_len")
-    n, k, t_len = loc_feat.shape
-    a = key.shape[2]
-    attn = out if out is not None else torch.empty((n, t_len), dtype=F32, device=key.device)
-    _chk(attn, F32, "attn", n * t_len)
-    L.check(L.load().e2e_attention_loc_step(L.ptr(key), L.ptr(query), L.ptr(loc_feat), L.ptr(enc_len), L.ptr(w_proj),
-                                           L.ptr(w_energy), float(b_energy), float(temperature), int(n), int(beam),
-                                           int(t_len), int(a), int(k), L.ptr(attn), _stream()))
-    return attn
-
-
 def attention_loc_full(key_t, value, query, prev_att, enc_len, w_conv, w_proj, w_energy, b_energy, temperature, beam,
                        n_run=None, hyps_per_unit=0, attn=None, ctx=None):
     """The whole location-aware attention step (conv + energies + masked softmax + context) for the first

@@ -208,27 +208,15 @@ int e2e_nbest_pack_ragged(int U, int B, int cap_in, const int *tok, const float 
                           const float *avg, const int *n, const int *slot, const long long *tok_off,
                           const int *cap, int *hdr, int *tok_out, int *sc_out, void *stream);
 
-/* (next) Fused location-aware attention energies + masked softmax for one
- * decode step.  Replaces LocationAwareAttention.forward minus the convolution
- * (src/module.py:1163-1168) and BaseAttention._attend minus the context product
- * (src/module.py:1109-1113):
- *   attn[n][t] = softmax_t( (b_e + sum_a w_e[a] * tanh(key[u][t][a] + query[n][a]
- *                            + tanh(sum_k w_proj[a][k] * loc_feat[n][k][t]))) / temperature ),  t < enc_len[u]
- * and exactly 0 for t >= enc_len[u]; u = n / B.
- *   key [U][T][A] (tanh(proj_k(enc)), src/asr.py:343), query [n_hyp][A] (tanh(proj_q(h)), src/asr.py:337),
- *   loc_feat [n_hyp][K][T] (loc_conv(prev_att), src/module.py:1163), w_proj [A][K], w_energy [A].
- *   Needs K <= 12 and A % 4 == 0. */
-int e2e_attention_loc_step(const float *key, const float *query, const float *loc_feat, const int *enc_len,
-                           const float *w_proj, const float *w_energy, float b_energy, float temperature,
-                           int n_hyp, int B, int T, int A, int K, float *attn, void *stream);
-
 /* (next) The WHOLE location-aware attention step in one kernel:
  * LocationAwareAttention.forward (src/module.py:1152-1173) including the location convolution
  * (Conv1d 1->K, W = 2*kernel_size+1 taps, zero padded, no bias; src/module.py:1140,1163) and
  * BaseAttention._attend (src/module.py:1109-1117) including the context product, for the first
  * n_run utterances x B beam slots (hypothesis n = u*B + b):
  *   feat[n][k][t] = sum_j w_conv[k][j] * prev_att[n][t + j - W/2]
- *   attn[n][t]    = as e2e_attention_loc_step, from feat;   exactly 0 for t >= enc_len[u]
+ *   attn[n][t]    = softmax_t( (b_e + sum_a w_e[a] * tanh(key[u][t][a] + query[n][a]
+ *                            + tanh(sum_k w_proj[a][k] * feat[n][k][t]))) / temperature ),  t < enc_len[u];
+ *                   exactly 0 for t >= enc_len[u]   (u = n / B)
  *   ctx[n][e]     = sum_{t < enc_len[u]} attn[n][t] * value[u][t][e]
  *   key_t [U][A][T] (the keys tanh(proj_k(enc)), src/asr.py:343, stored CHANNEL-major), value [U][T][E],
  *   query [n][A], prev_att [n][T] (zero beyond enc_len[u]),

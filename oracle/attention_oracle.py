@@ -4,7 +4,7 @@ Follows ``/root/reference/src/module.py``: ``LocationAwareAttention.forward`` (:
 the convolution, whose output is an input here) and ``BaseAttention._attend`` (:1109-1117, minus the
 context product), with ``compute_mask`` (:1100-1107).  Batched over hypotheses n = u*B + b; checked
 against the product's own reference-shaped module in tests/test_oracle_golden.py and used as the
-checker of ``e2e_attention_loc_step`` in tests/test_gpu_kernels.py.
+checker of ``e2e_attention_loc_full`` in tests/test_gpu_kernels.py.
 """
 import numpy as np
 import torch

@@ -38,10 +38,11 @@ EOS_ID = 1
 
 class Beam:
     """One partial transcript with everything needed to resume it."""
-    __slots__ = ("tokens", "scores", "dec_state", "att_map", "lm_state", "ctc_state", "ctc_prob")
+    __slots__ = ("tokens", "scores", "dec_state", "att_map", "lm_state", "ctc_state", "ctc_prob", "_cum")
 
-    def __init__(self, tokens, scores, dec_state, att_map, lm_state, ctc_state, ctc_prob):
+    def __init__(self, tokens, scores, dec_state, att_map, lm_state, ctc_state, ctc_prob, cum=None):
         self.tokens, self.scores = tokens, scores            # lists of 0-d tensors (ints / fp32)
+        self._cum = cum                                      # (len(scores), their left-to-right sum) if already known
         self.dec_state, self.att_map = dec_state, att_map
         if isinstance(lm_state, tuple):
             lm_state = (lm_state[0].cpu(), lm_state[1].cpu())
@@ -57,9 +58,16 @@ class Beam:
     # reference name, so results can be compared field by field
     outIndex = ids
 
+    def score_sum(self):
+        """python sum(): 0 + s0 + s1 + ... one fp32 add at a time, left to right (decode.py:214-217).  A child's sum is
+        its parent's sum plus one more add, so the running value is carried along (same adds, same order, same bits)
+        instead of being re-added from scratch for every sort key — the long-form cases would otherwise cost O(S^2)."""
+        if self._cum is None or self._cum[0] != len(self.scores):
+            self._cum = (len(self.scores), sum(self.scores))
+        return self._cum[1]
+
     def mean_score(self):
-        # python sum(): 0 + s0 + s1 + ... one fp32 add at a time (decode.py:214-217)
-        return sum(self.scores) / len(self.scores)
+        return self.score_sum() / len(self.scores)
 
     avgScore = mean_score
 
@@ -83,7 +91,8 @@ def _expand(parent, top_ids, top_vals, dec_state, att_map, lm_state, ctc_state, 
         if ctc_state is not None:
             j = cands.index(tok)            # ValueError if the winner was not a CTC candidate (decode.py:252)
             st, pr = ctc_state[j, :, :], ctc_prob[j]
-        children.append(Beam(toks, scs, dec_state, att_map, lm_state, st, pr))
+        cum = (len(scs), (parent.score_sum() + scs[-1]) if parent.scores else (0 + scs[-1]))
+        children.append(Beam(toks, scs, dec_state, att_map, lm_state, st, pr, cum))
     if closing is not None:
         parent.tokens.append(torch.tensor(EOS_ID))
         parent.scores.append(closing)

@@ -241,3 +241,73 @@ def test_decode_large_vocab_and_wide_beam_match_oracle(cuda, vocab, beam, lm_w, 
         same, ties = same + s, ties + t
     print("V %d beam %d: identical 1-best %d/%d, ties %d" % (vocab, beam, same, len(lens), ties))
     assert same >= len(lens) - 1
+
+
+class _COracleScorer:
+    """The prefix scorer interface of oracle/ctc_prefix_oracle.py on top of the plain-C oracle (bit-identical, tests/
+    test_oracle_golden.py; its frame loop is compiled, which the long-form case needs)."""
+
+    def __init__(self, x):
+        from oracle import c_oracle as CO
+        self.CO, self.x = CO, np.ascontiguousarray(x[0], dtype=np.float32)
+        self.input_length, self.odim = self.x.shape
+
+    def init_state(self):
+        return self.CO.blank_state(self.x)
+
+    def cheap_compute(self, g, r_prev, candidates):
+        return self.CO.extend(self.x, len(g), g[-1] if g else 0, r_prev, candidates)
+
+
+def _oracle_nbest_c(asr, lm, feat, n, beam, lm_w, ctc_w, max_ratio):
+    from oracle import beam_oracle as BO
+    asr, lm = _cpu_copy(asr), _cpu_copy(lm)
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)                 # batch-1 modules of a few dozen units: intra-op threading only costs
+    try:
+        with torch.no_grad():
+            nb = BO.decode_utterance(asr, feat[None, :n], torch.LongTensor([n]), beam, 0.01, max_ratio, lm=lm if lm_w > 0 else None,
+                                     lm_weight=lm_w, ctc_weight=ctc_w, scorer_cls=_COracleScorer)
+    finally:
+        torch.set_num_threads(threads)
+    return BO.nbest_as_arrays(nb)
+
+
+def test_decode_subword_vocab_10000_matches_oracle(cuda):
+    """BASELINE cfg3 end to end at its vocabulary size: V = 10000 (column-gather variant of the fused prefix kernel, the
+    one-CTA-per-row posterior kernel, 10k-wide candidate / combine kernels and RNNLM output), beam 8 + LM,
+    max_len_ratio 0.07 (config/libri/decode_example.yaml:13), against the per-hypothesis CPU oracle."""
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth
+    asr, lm, lm_path, lm_cfg = _models(vocab=10000)
+    lens = [200, 148, 120]
+    feat, fl = synth.padded_batch(list(range(len(lens))), lens)
+    dec = BeamDecoder(asr, None, 8, 0.01, 0.07, lm_path=lm_path, lm_config=lm_cfg, lm_weight=0.5, ctc_weight=0.5).to(cuda)
+    out = dec.decode_batch(feat.to(cuda), fl.to(cuda))
+    same = ties = 0
+    for k, n in enumerate(lens):
+        ora = _oracle_nbest_c(asr, lm, feat[k], n, 8, 0.5, 0.5, 0.07)
+        assert len(out[k]) == len(ora)
+        s, t = _compare(out[k], ora, "V 10000 utt %d" % k)
+        same, ties = same + s, ties + t
+    print("V 10000 beam 8: identical 1-best %d/%d, ties %d" % (same, len(lens), ties))
+    assert same + ties == len(lens)
+
+
+def test_decode_longform_875_frames_beam16_matches_oracle(cuda):
+    """BASELINE cfg4 end to end at its sizes: a 35-s utterance (3500 input frames, 875 encoder frames, 700 decode steps),
+    beam 16 (24 CTC candidates: 2 state + 2 helper + 12 psi warps per utterance in the fused prefix kernel) + LM, decoded
+    together with a shorter one, against the per-hypothesis CPU oracle (small modules so that it finishes in seconds)."""
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth
+    asr, lm, lm_path, lm_cfg = _models()
+    lens = [3500, 400]
+    feat, fl = synth.padded_batch([40, 41], lens)
+    dec = BeamDecoder(asr, None, 16, 0.01, 0.2, lm_path=lm_path, lm_config=lm_cfg, lm_weight=0.3, ctc_weight=0.5).to(cuda)
+    out = dec.decode_batch(feat.to(cuda), fl.to(cuda))
+    same = ties = 0
+    for k, n in enumerate(lens):
+        ora = _oracle_nbest_c(asr, lm, feat[k], n, 16, 0.3, 0.5, 0.2)
+        assert len(out[k]) == len(ora)
+        s, t = _compare(out[k], ora, "long form utt %d (%d frames)" % (k, n))
+        same, ties = same + s, ties + t
+    print("long form (875 encoder frames, beam 16): identical 1-best %d/%d, ties %d" % (same, len(lens), ties))
+    assert same + ties == len(lens)

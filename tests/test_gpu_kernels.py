@@ -405,33 +405,6 @@ def test_prefix_too_long_sets_status(cuda):
 # ----------------------------------------------------------------------------------------------
 # f-1: fused location-aware attention step
 # ----------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n_utts,beam,t_len,dim,n_filt", [(3, 8, 180, 300, 10), (2, 2, 37, 24, 4), (1, 16, 875, 300, 10), (4, 4, 300, 128, 12)])
-def test_attention_loc_step_matches_oracle(cuda, n_utts, beam, t_len, dim, n_filt):
-    """attn within 5e-6 abs of the fp32 CPU restatement (MUFU-based tanh, fp32 softmax; the fixture uses
-    4x larger energy weights than init gives); masked frames exactly 0."""
-    ops, _ = _ops()
-    from oracle import attention_oracle as AO
-    g = torch.Generator().manual_seed(t_len + dim)
-    n = n_utts * beam
-    key = torch.tanh(torch.randn(n_utts, t_len, dim, generator=g))
-    query = torch.tanh(torch.randn(n, dim, generator=g))
-    prev = torch.softmax(torch.randn(n, t_len, generator=g) * 2, -1)
-    conv_w = torch.randn(n_filt, 1, 21, generator=g) * 0.3
-    feat = torch.nn.functional.conv1d(prev[:, None, :], conv_w, padding=10).contiguous()
-    w_proj = torch.randn(dim, n_filt, generator=g) / n_filt ** 0.5
-    w_e = torch.randn(dim, generator=g) / dim ** 0.5 * 4
-    enc_len = torch.tensor([max(1, t_len - 7 * i) for i in range(n_utts)], dtype=torch.int32)
-    want = AO.loc_attention_step(key, query, feat, enc_len, w_proj, w_e, 0.25, 0.5, beam)
-    got = ops.attention_loc_step(key.to(cuda), query.to(cuda), feat.to(cuda), enc_len.to(cuda), w_proj.to(cuda),
-                                 w_e.to(cuda), 0.25, 0.5, beam).cpu()
-    err = (got - want).abs().max().item()
-    print("attention step U=%d B=%d T=%d A=%d: max |gpu-oracle| = %.3g" % (n_utts, beam, t_len, dim, err))
-    assert err < 5e-6
-    for u in range(n_utts):
-        assert (got[u * beam:(u + 1) * beam, int(enc_len[u]):] == 0).all()
-    assert torch.allclose(got.sum(-1), torch.ones(n), atol=1e-5)
-
-
 @pytest.mark.parametrize("n_utts,beam,t_len,dim,n_filt,half,e_dim", [(3, 8, 180, 300, 10, 100, 640), (2, 2, 37, 24, 4, 10, 40),
                                                                      (1, 16, 875, 300, 10, 100, 640), (4, 3, 300, 128, 12, 25, 96),
                                                                      (2, 1, 50, 32, 7, 3, 17)])
