@@ -334,7 +334,8 @@ def run_b200(args):
                                "beam 8, ctc 0.5, lm 0.5, max_len_ratio 0.2, %d utts/GPU dev-clean-like lengths, random init" % args.n_utts,
                    "utterances": n_total, "batches_per_gpu": len(batches), "max_utts_per_batch": args.max_utts,
                    "prefix_fast_math": bool(args.fast_math), "prefix_math": "mufu" if args.fast_math else dec.prefix_math, "skip_dead_rows": not args.write_dead_rows,
-                   "h2d": "valid frames only, one copy per utterance" if args.ragged_h2d else "padded [U,Lmax,D] tensor, one copy",
+                   "h2d": "pinned host features, valid frames only, one copy per utterance on a copy stream, pipelined under the encoder "
+                          "in 128-utterance chunks (BeamDecoder.decode_batch_from_host)" if args.ragged_h2d else "padded [U,Lmax,D] tensor, one copy",
                    "lm_gemm_operands": dec.lm_split, "vgg_gemm_operands": dec.vgg_split,
                    "l2": "inputs (%.1f GB features + GB-scale prefix states per batch) exceed the 126 MB L2; no flush needed" % (in_bytes / 1e9),
                    "parallelism": "utterance shards x%d, one all-gather of the ragged N-best buffer (packed on the device, one pinned read-back)" % world},
@@ -428,23 +429,64 @@ class ReferenceCpu:
         return time.time() - t0, res
 
 
+def _port_worker(job):
+    uid, n = job
+    import torch as th
+    th.set_num_threads(1)
+    from oracle import beam_oracle as BO
+    from e2e_asr_pytorch_b200 import synth
+    global _PORT_MODELS
+    try:
+        asr, lm = _PORT_MODELS
+    except NameError:
+        asr, lm = synth.build_asr(VOCAB, seed=0), synth.build_lm(VOCAB, seed=1)
+        _PORT_MODELS = (asr, lm)
+    with th.no_grad():
+        nb = BO.decode_utterance(asr, synth.utterance(uid, n)[None], th.LongTensor([n]), BEAM, MIN_RATIO, MAX_RATIO, lm=lm,
+                                 lm_weight=LM_W, ctc_weight=CTC_W)
+    return ("utt%d" % uid, [b.ids for b in nb], [])
+
+
+class PortCpu:
+    """Fallback when oracle/_ref did not reach this machine: the oracle PORT of the reference (oracle/beam_oracle.py with the
+    product's model.py modules), one utterance per forked worker process.  ``kind`` = "port" in the JSON line."""
+    kind = "port"
+
+    def run(self, jobs, n_jobs, threads):
+        import multiprocessing as mp
+        jobs = sorted(jobs, key=lambda j: -j[1])
+        with mp.get_context("fork").Pool(n_jobs) as pool:
+            t0 = time.time()
+            res = pool.map(_port_worker, jobs, chunksize=1)
+            return time.time() - t0, res
+
+
+def cpu_arm():
+    """The unmodified reference if it can be imported here (oracle/_ref or /root/reference), else the oracle port."""
+    try:
+        return ReferenceCpu()
+    except Exception as e:
+        sys.stderr.write("bench.py: the staged reference is not importable (%s); timing the oracle port instead\n" % (e,))
+        return PortCpu()
+
+
 def cpu_baseline(args, sample_utts=None):
     """Bounded CPU figure printed beside the B200 line: one median-length utterance per core."""
     cores = len(os.sched_getaffinity(0))
     procs = max(1, min(cores, args.cpu_procs or cores))
     n_jobs = sample_utts or procs
-    ref = ReferenceCpu()
+    ref = cpu_arm()
     frames = args.cpu_frames or 640
     jobs = [(100000 + k, frames) for k in range(n_jobs)]
     ref.run([(200000 + k, 80) for k in range(procs)], procs, 1)                   # spawns the workers, imports, first touch
     wall, _ = ref.run(jobs, procs, 1)
-    return {"value": n_jobs / wall, "unit": "utts/s", "cores": procs, "kind": "reference", "cpu": cpu_model_name(),
+    return {"value": n_jobs / wall, "unit": "utts/s", "cores": procs, "kind": "reference" if ref.kind != "port" else "port", "cpu": cpu_model_name(),
             "sample": "%d synthetic utts of %d input frames (%.1f s audio%s) each; the unmodified reference BeamDecoder (%s) through "
                       "bin/test_asr.py::beam_decode and joblib.Parallel(n_jobs=%d), 1 torch thread per worker, %.1f s wall; the CPU cost "
                       "grows ~L^2, so the median length flatters the CPU by ~1.8x against the workload's mean cost — "
                       "`bench.py --impl reference` decodes a length-stratified sample of the set itself"
                       % (n_jobs, frames, frames / 100.0, MEDIAN_NOTE if frames == 640 else "",
-                         "oracle/_ref" if ref.kind == "staged" else "/root/reference", procs, wall),
+                         {"staged": "oracle/_ref", "live": "/root/reference", "port": "NOT AVAILABLE HERE: oracle port, oracle/beam_oracle.py"}[ref.kind], procs, wall),
             "cand_frames_per_s": sum(cand_frames(n) for _, n in jobs) / wall}
 
 
@@ -460,7 +502,7 @@ def run_reference(args):
         jobs = [(100000 + k, args.cpu_frames) for k in range(per_step * args.steps)]
     else:
         jobs = [(i, int(lengths[i])) for i in stratified_sample(lengths, per_step * args.steps)]
-    ref = ReferenceCpu()
+    ref = cpu_arm()
     for _ in range(max(1, args.warmup)):                                          # workers up, modules imported, caches warm
         ref.run([(200000 + k, 80) for k in range(procs)], procs, 1)
     # best effort: one worker per core, one torch thread each; the K steps' samples are ONE joblib.Parallel region
@@ -476,9 +518,9 @@ def run_reference(args):
               "unmodified reference (%s: src/decode.py BeamDecoder + src/ctc.py CTCPrefixScore) through bin/test_asr.py::beam_decode "
               "and joblib.Parallel(n_jobs=%d), 1 torch thread per worker, longest first"
               % (len(jobs), what, lens[0], lens[-1], int(np.mean(lens)), per_step,
-                 "oracle/_ref" if ref.kind == "staged" else "/root/reference", procs))
+                 {"staged": "oracle/_ref", "live": "/root/reference", "port": "NOT AVAILABLE HERE: oracle port, oracle/beam_oracle.py"}[ref.kind], procs))
     shipped = None
-    if not args.no_as_shipped:
+    if not args.no_as_shipped and ref.kind != "port":
         # as shipped (script/test.sh:15): --njobs 4, torch threads left at the library default; on a smaller stratified sample
         if args.cpu_frames:
             sjobs = [(300000 + k, args.cpu_frames) for k in range(args.as_shipped_sample)]
@@ -499,7 +541,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg2: char V=31 VGG+BLSTM CTC-attention (librispeech_asr.yaml dims, vgg=1) + 4x1024 RNNLM, "
                                "beam 8, ctc 0.5, lm 0.5, max_len_ratio 0.2, dev-clean-like lengths, random init; bounded sample: " + sample},
-        "cpu_baseline": {"value": value, "unit": "utts/s", "cores": procs, "kind": "reference", "cpu": cpu_model_name(),
+        "cpu_baseline": {"value": value, "unit": "utts/s", "cores": procs, "kind": "reference" if ref.kind != "port" else "port", "cpu": cpu_model_name(),
                          "sample": sample, "cand_frames_per_s": units / wall, "wall_s": wall, "as_shipped": shipped},
         "e2e": {"value": value, "unit": "utts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -522,8 +564,10 @@ def main():
                     help="operand format of the VGG convolution GEMMs (default: the decoder's, bf16x3)")
     ap.add_argument("--prefix-math", default="", choices=["", "lut", "poly", "poly_estrin"],
                     help="log-add-exp evaluator of the prefix-score kernel (default: the decoder's, lut)")
-    ap.add_argument("--ragged-h2d", action="store_true",
-                    help="e2e leg: copy only the valid frames of every utterance (BeamDecoder.decode_batch_from_host)")
+    ap.add_argument("--ragged-h2d", action="store_true", help="(default now; kept for old command lines)")
+    ap.add_argument("--padded-h2d", action="store_true",
+                    help="e2e leg: copy the zero-padded [U,Lmax,D] tensor in one piece before decode_batch instead of the valid frames "
+                         "only, pipelined under the encoder (BeamDecoder.decode_batch_from_host, the default)")
     ap.add_argument("--ragged-gather", action="store_true", help="(default now; kept for old command lines)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0)
@@ -533,6 +577,7 @@ def main():
     ap.add_argument("--no-as-shipped", action="store_true", help="reference arm: skip the as-shipped (--njobs 4) measurement")
     ap.add_argument("--as-shipped-sample", type=int, default=8, help="reference arm: utterances of the as-shipped measurement")
     args = ap.parse_args()
+    args.ragged_h2d = not args.padded_h2d
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -7,8 +7,54 @@ namespace e2e {
 
 constexpr int kRowWarps = 8;   // rows (one per warp) per CTA
 
-// One warp per output row (t,u).  Lane l owns the 4-column groups l, l+32, ... of the row.
-// kCached: the whole row fits in one group per lane (Vp <= 128) and stays in registers.
+// Narrow rows (Vp <= 128, e.g. the 31-token character vocabulary): a row is owned by a group of G = Vp/4 lanes (rounded up
+// to a power of two), each lane holding 4 columns in registers, so a warp carries 32/G rows (4 rows at Vp = 32): the
+// max / sum-exp reductions are log2(G) shuffles, and the warp's rows leave as one contiguous run of 16-byte stores
+// (consecutive rows t*U+u are consecutive in the frame-major tensor).
+template <int G>
+__global__ void __launch_bounds__(256)
+ctc_log_softmax_narrow_kernel(const float *__restrict__ logits, int U, int Tmax, int V, const int *__restrict__ enc_len,
+                              int apply_relu, float *__restrict__ x, int Vp)
+{
+    constexpr int kRowsPerWarp = 32 / G;
+    const int lane = threadIdx.x & 31, sub = lane / G, gl = lane % G;
+    const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kRowsPerWarp + sub;   // = t*U + u
+    const bool valid_row = row < (long long)Tmax * U;
+    const int t = valid_row ? (int)(row / U) : 0, u = valid_row ? (int)(row % U) : 0;
+    const int tu = enc_len ? enc_len[u] : Tmax;
+    const bool live = valid_row && t < tu;
+    const int v0 = gl * 4;
+    const float *__restrict__ in = logits + ((long long)u * Tmax + t) * V;
+    float a[4];
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float val = -INFINITY;
+        if (live && v0 + k < V) {
+            val = __ldg(in + v0 + k);
+            if (apply_relu) val = fmaxf(val, 0.0f);
+        }
+        a[k] = val;
+        m = fmaxf(m, val);
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(E2E_FULL_MASK, m, o));
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s += (a[k] == -INFINITY) ? 0.0f : expf(a[k] - m);
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(E2E_FULL_MASK, s, o);
+    const float ls = logf(s);
+    if (valid_row && v0 < Vp) {
+        float o4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o4[k] = (live && v0 + k < V) ? (a[k] - m) - ls : E2E_CTC_LOGZERO;
+        reinterpret_cast<float4 *>(x + row * Vp)[gl] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    }
+}
+
+// One warp per output row (t,u); lane l owns the 4-column groups l, l+32, ... of the row (rows of any width; the fallback
+// for rows too wide for shared-memory staging).
 template <bool kCached>
 __global__ void __launch_bounds__(kRowWarps * 32)
 ctc_log_softmax_kernel(const float *__restrict__ logits, int U, int Tmax, int V, const int *__restrict__ enc_len,
@@ -176,9 +222,20 @@ extern "C" int e2e_ctc_log_softmax(const float *logits, int U, int Tmax, int V, 
     const long long rows = (long long)Tmax * U;
     const unsigned blocks = (unsigned)((rows + kRowWarps - 1) / kRowWarps);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (Vp <= 128)
-        ctc_log_softmax_kernel<true><<<blocks, kRowWarps * 32, 0, st>>>(logits, U, Tmax, V, enc_len, apply_relu, x, Vp);
-    else if ((size_t)Vp * 4 <= 160 * 1024 && rows <= 0x7fffffffLL) {
+    if (Vp <= 128) {
+        const int groups = Vp / 4;
+        const int G = groups <= 1 ? 1 : groups <= 2 ? 2 : groups <= 4 ? 4 : groups <= 8 ? 8 : groups <= 16 ? 16 : 32;
+        const long long per_cta = (long long)8 * (32 / G);                      // 8 warps per CTA
+        const unsigned nb = (unsigned)((rows + per_cta - 1) / per_cta);
+        switch (G) {
+            case 1: ctc_log_softmax_narrow_kernel<1><<<nb, 256, 0, st>>>(logits, U, Tmax, V, enc_len, apply_relu, x, Vp); break;
+            case 2: ctc_log_softmax_narrow_kernel<2><<<nb, 256, 0, st>>>(logits, U, Tmax, V, enc_len, apply_relu, x, Vp); break;
+            case 4: ctc_log_softmax_narrow_kernel<4><<<nb, 256, 0, st>>>(logits, U, Tmax, V, enc_len, apply_relu, x, Vp); break;
+            case 8: ctc_log_softmax_narrow_kernel<8><<<nb, 256, 0, st>>>(logits, U, Tmax, V, enc_len, apply_relu, x, Vp); break;
+            case 16: ctc_log_softmax_narrow_kernel<16><<<nb, 256, 0, st>>>(logits, U, Tmax, V, enc_len, apply_relu, x, Vp); break;
+            default: ctc_log_softmax_narrow_kernel<32><<<nb, 256, 0, st>>>(logits, U, Tmax, V, enc_len, apply_relu, x, Vp); break;
+        }
+    } else if ((size_t)Vp * 4 <= 160 * 1024 && rows <= 0x7fffffffLL) {
         const size_t smem = (size_t)Vp * 4;
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(ctc_log_softmax_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -151,6 +151,7 @@ class BeamDecoder(nn.Module):
         # bin/test_asr.py:108,138 deep-copies and pickles the decoder: drop the per-device caches
         d = self.__dict__.copy()
         d["_stepper"], d["prefix_events"] = None, []
+        d.pop("_copier", None)
         return d
 
     def create_msg(self):
@@ -167,12 +168,15 @@ class BeamDecoder(nn.Module):
         assert audio_feature.shape[0] == 1, "Batchsize == 1 is required for beam search"   # decode.py:67
         return self.decode_batch(audio_feature, feature_len)[0]
 
+    ENCODER_CHUNK = 128       # utterances per encoder chunk (stepper.encode); the host->device copy is pipelined in the same units
+
     @torch.no_grad()
     def decode_batch_from_host(self, audio_feature, feature_len, device, return_arrays=False):
-        """``decode_batch`` for PINNED HOST features [U,Lmax,D] (zero padded) and host lengths [U]: only the valid
-        frames of every utterance cross the bus (one asynchronous copy per utterance on the current stream; a
-        dev-clean-like set is 4.6x smaller than its padded tensor), the padding is a device-side memset.
-        ``last_h2d_bytes`` holds the bytes copied."""
+        """``decode_batch`` for PINNED HOST features [U,Lmax,D] (zero padded) and host lengths [U].  Only the valid frames
+        of every utterance cross the bus (a dev-clean-like set is 4.6x smaller than its padded tensor; the padding is a
+        device-side memset), one asynchronous copy per utterance, issued longest first on a COPY STREAM in chunks of
+        ``ENCODER_CHUNK`` utterances — the order and the units in which the encoder consumes them, so the encoder starts
+        on the first chunk while the rest is still in flight (one event per chunk).  ``last_h2d_bytes`` holds the bytes copied."""
         if audio_feature.is_cuda:
             return self.decode_batch(audio_feature, feature_len, return_arrays)
         if not audio_feature.is_pinned():
@@ -180,16 +184,54 @@ class BeamDecoder(nn.Module):
                              "would turn every copy into a synchronous one")
         dev = torch.device(device)
         lens = [int(n) for n in feature_len]
-        if audio_feature.dim() != 3 or len(lens) != audio_feature.shape[0] or (lens and max(lens) > audio_feature.shape[1]):
+        n_utts = len(lens)
+        if audio_feature.dim() != 3 or n_utts != audio_feature.shape[0] or (lens and max(lens) > audio_feature.shape[1]):
             raise ValueError("decode_batch_from_host: features [U,Lmax,D] and lengths [U] disagree")
+        # decode order (decode_batch's own: longest output first, ties by index): rows arrive already sorted
+        max_np = np.array([int(np.ceil(n * self.max_len_ratio)) for n in lens], dtype=np.int64)
+        order = np.lexsort((np.arange(n_utts), -max_np)) if n_utts else np.zeros(0, dtype=np.int64)
+        inverse = np.argsort(order)
         with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
             feat_dev = torch.zeros(audio_feature.shape, dtype=torch.float32, device=dev)
-            for u, n in enumerate(lens):
-                if n > 0:
-                    feat_dev[u, :n].copy_(audio_feature[u, :n], non_blocking=True)
-            len_dev = feature_len.to(dev, non_blocking=True)
+            len_dev = torch.as_tensor(np.asarray(lens, dtype=np.int64)[order]).to(dev, non_blocking=True)
+            copier = self._copy_stream(dev)
+            copier.wait_stream(main)                                   # the memset above
+            feat_dev.record_stream(copier)
+            events = []
+            with torch.cuda.stream(copier):
+                for lo in range(0, n_utts, self.ENCODER_CHUNK):
+                    for row in range(lo, min(n_utts, lo + self.ENCODER_CHUNK)):
+                        u = int(order[row])
+                        if lens[u] > 0:
+                            feat_dev[row, :lens[u]].copy_(audio_feature[u, :lens[u]], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copier)
+                    events.append(ev)
             self.last_h2d_bytes = sum(lens) * audio_feature.shape[2] * 4 + feature_len.numel() * feature_len.element_size()
-            return self.decode_batch(feat_dev, len_dev, return_arrays)
+            enc_mod = self.asr.encoder
+
+            def rows_ready(lo, hi):          # the current stream waits for the copies of rows [lo, hi)
+                for c in range(lo // self.ENCODER_CHUNK, (max(hi, lo + 1) - 1) // self.ENCODER_CHUNK + 1):
+                    torch.cuda.current_stream(dev).wait_event(events[c])
+
+            enc_mod.chunk_ready = rows_ready          # stepper.encode / Encoder.forward_ragged_packed call it before touching rows
+            try:
+                out = self._decode_batch(feat_dev, len_dev, return_arrays)
+            finally:
+                enc_mod.chunk_ready = None
+                main.wait_stream(copier)
+            if return_arrays:
+                sel = torch.as_tensor(inverse, device=out[0].device)
+                return tuple(a.index_select(0, sel) for a in out)
+            return [out[int(k)] for k in inverse]
+
+    def _copy_stream(self, dev):
+        st = getattr(self, "_copier", None)
+        if st is None or st[0] != dev:
+            st = (dev, torch.cuda.Stream(device=dev))
+            self._copier = st
+        return st[1]
 
     @torch.no_grad()
     def decode_batch(self, audio_feature, feature_len, return_arrays=False):

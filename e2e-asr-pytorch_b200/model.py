@@ -376,8 +376,11 @@ class Encoder(nn.Module):
         n_utts = x.shape[0]
         front = self.layers[0] if isinstance(self.layers[0], VGGFrontEnd) else None
         packs, tls = [], []
+        ready = getattr(self, "chunk_ready", None)      # decode_batch_from_host: rows [lo, hi) have arrived from the host
         for lo in range(0, n_utts, chunk):
             hi = min(n_utts, lo + chunk)
+            if ready is not None:
+                ready(lo, hi)
             l_max = int(lens_host[lo:hi].max())
             xc, lc = x[lo:hi, :l_max], x_len[lo:hi]
             if front is not None:

@@ -309,11 +309,17 @@ class BatchedStepper:
         for layer in getattr(enc_mod, "layers", []):
             if hasattr(layer, "conv_split_format"):
                 layer.conv_split_format = self.vgg_split
+        packed = (n_utts > 1 and self.split_conv and feats.is_cuda and hasattr(enc_mod, "forward_ragged_packed")
+                  and enc_mod.packed_supported())
+        ready = getattr(enc_mod, "chunk_ready", None)
+        if ready is not None and not packed:
+            ready(0, n_utts)                      # features still arriving from the host (decode_batch_from_host): only the
+                                                  # packed path below consumes them chunk by chunk
         if n_utts == 1:
             # one utterance: the plain module call, on the valid frames only — zero padding would otherwise reach the
             # backward LSTM direction (the reference's batch-1 call is never padded, bin/test_asr.py:159-167)
             enc, enc_len = enc_mod(feats[:, :int(lens[0])], lens)
-        elif self.split_conv and feats.is_cuda and hasattr(enc_mod, "forward_ragged_packed") and enc_mod.packed_supported():
+        elif packed:
             # device path: split convolutions, packed frames, persistent recurrent kernel (model.py)
             enc_mod.split_conv = True
             enc, enc_len = enc_mod.forward_ragged_packed(feats, lens, chunk)

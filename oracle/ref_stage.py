@@ -2,9 +2,11 @@
 
 The reference (DanielLin94144/E2E-ASR-Pytorch) is Python.  Its decode path — ``src/ctc.py``, ``src/decode.py`` and the
 modules they import, plus the caller ``bin/test_asr.py`` — is byte-compiled from the sources where they lie under
-``/root/reference`` into sourceless ``.pyc`` files under ``oracle/_ref/`` (git-ignored, NOT gpurun-ignored: it travels to
+``/root/reference`` into sourceless bytecode files under ``oracle/_ref/`` (git-ignored, NOT gpurun-ignored: it travels to
 the GPU box like a built ``.so``).  No reference source text enters the repository; the outputs are CPython bytecode
-of this image's interpreter, and ``MANIFEST.json`` records the sha256 of every source file they were made from.
+of this image's interpreter (the bytes of a ``.pyc``, stored with the extension ``.refc`` because snapshot tools drop
+``*.pyc``; ``oracle/refload.py`` has the importer), and ``MANIFEST.json`` records the sha256 of every source file they were
+made from.
 
 Users (and nobody else): ``oracle/refload.py`` → the ``not gpu`` pin tests, ``bench.py --impl reference`` and
 ``bench.py``'s ``cpu_baseline`` leg (the CPU arm the B200 path is timed against), and the drop-in test that drives
@@ -24,6 +26,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = os.environ.get("E2E_REFERENCE_ROOT", "/root/reference")
 OUT = os.path.join(_HERE, "_ref")
 # the decode path and its caller: nothing else is staged
+EXT = ".refc"
 FILES = ["src/ctc.py", "src/decode.py", "src/asr.py", "src/module.py", "src/lm.py", "src/util.py", "bin/__init__.py", "bin/test_asr.py"]
 
 
@@ -32,7 +35,7 @@ def source_available():
 
 
 def staged():
-    return os.path.isfile(os.path.join(OUT, "MANIFEST.json")) and os.path.isfile(os.path.join(OUT, "src", "decode.pyc"))
+    return os.path.isfile(os.path.join(OUT, "MANIFEST.json")) and os.path.isfile(os.path.join(OUT, "src", "decode" + EXT))
 
 
 def _sha(path):
@@ -49,18 +52,18 @@ def stage(force=False):
     if not force and staged():
         try:
             have = json.load(open(man_path))
-            if have.get("sha256") == want and have.get("magic") == importlib.util.MAGIC_NUMBER.hex():
+            if have.get("sha256") == want and have.get("magic") == importlib.util.MAGIC_NUMBER.hex() and have.get("ext") == EXT:
                 return have
         except Exception:
             pass
     for f in FILES:
-        dst = os.path.join(OUT, f[:-3] + ".pyc")
+        dst = os.path.join(OUT, f[:-3] + EXT)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         # dfile: the path shown in tracebacks (there is no source file to open on the GPU box)
         py_compile.compile(os.path.join(REF_SRC, f), cfile=dst, dfile="reference/" + f, doraise=True, optimize=0,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
     man = {"what": "CPython bytecode of the unmodified reference's decode path (no sources)", "from": REF_SRC,
-           "python": sys.version.split()[0], "magic": importlib.util.MAGIC_NUMBER.hex(), "sha256": want}
+           "python": sys.version.split()[0], "magic": importlib.util.MAGIC_NUMBER.hex(), "ext": EXT, "sha256": want}
     with open(man_path, "w") as f:
         json.dump(man, f, indent=1)
     return man

@@ -5,8 +5,8 @@ Two places it can come from:
 * ``/root/reference`` — the live source tree, present only in the build container.  Used by
   ``tools/make_golden.py`` (fixture generation) and by the ``not gpu`` tests that pin the restatements
   in ``oracle/`` against the reference.
-* ``oracle/_ref/`` — the same files byte-compiled by ``oracle/ref_stage.py`` (sourceless ``.pyc``,
-  git-ignored, shipped to the GPU box).  Used there by ``bench.py --impl reference``, ``bench.py``'s
+* ``oracle/_ref/`` — the same files byte-compiled by ``oracle/ref_stage.py`` (sourceless bytecode with the
+  extension ``.refc``, git-ignored, shipped to the GPU box; imported through the small finder below).  Used there by ``bench.py --impl reference``, ``bench.py``'s
   ``cpu_baseline`` leg and the drop-in test.  TorchScript needs source text, so the two
   ``torch.jit.ScriptModule`` classes of ``src/module.py`` (liGRU, not on the decode path) are defined with
   scripting switched off for the duration of the import; nothing else differs.
@@ -45,6 +45,46 @@ def _stub_matplotlib():
         sys.modules["matplotlib.pyplot"] = plt
 
 
+class _StagedFinder:
+    """Meta-path finder / loader for the staged reference: module ``a.b`` <- ``oracle/_ref/a/b.refc`` (the bytes of a
+    .pyc: 16-byte header + marshalled code); ``a`` alone is a namespace-like package rooted at ``oracle/_ref/a``."""
+
+    def __init__(self, root):
+        self.root = root
+
+    def _path(self, name):
+        return os.path.join(self.root, *name.split("."))
+
+    def find_spec(self, name, path=None, target=None):
+        import importlib.machinery as M
+        if name.split(".")[0] not in ("src", "bin"):
+            return None
+        base = self._path(name)
+        if os.path.isfile(base + ref_stage.EXT):
+            return M.ModuleSpec(name, self, origin=base + ref_stage.EXT)
+        if os.path.isfile(os.path.join(base, "__init__" + ref_stage.EXT)):
+            spec = M.ModuleSpec(name, self, origin=os.path.join(base, "__init__" + ref_stage.EXT), is_package=True)
+            spec.submodule_search_locations = [base]
+            return spec
+        if os.path.isdir(base):
+            spec = M.ModuleSpec(name, self, origin=None, is_package=True)
+            spec.submodule_search_locations = [base]
+            return spec
+        return None
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        import marshal
+        origin = module.__spec__.origin
+        if origin is None:
+            return                                       # a directory without __init__: nothing to run
+        with open(origin, "rb") as f:
+            data = f.read()
+        exec(marshal.loads(data[16:]), module.__dict__)
+
+
 class _NoScript:
     """torch.jit scripting off while sourceless modules are imported (TorchScript wants source text)."""
 
@@ -70,13 +110,15 @@ def _root(staged):
         if not staged_available():
             raise RuntimeError("oracle/_ref is not built: run __graft_entry__.build() where /root/reference exists")
         root = ref_stage.OUT
+        if not any(isinstance(f, _StagedFinder) for f in sys.meta_path):
+            sys.meta_path.insert(0, _StagedFinder(root))
     else:
         if not available():
             raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
         root = REFERENCE_ROOT
         sys.dont_write_bytecode = True      # the reference tree is read-only
     _stub_matplotlib()
-    if root not in sys.path:
+    if not staged and root not in sys.path:
         sys.path.insert(0, root)
     _loaded = (kind, root)
     return _loaded

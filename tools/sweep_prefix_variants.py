@@ -9,6 +9,7 @@ Build a variant next to the product library (git-ignored; it travels to the GPU 
 
     python tools/sweep_prefix_variants.py              # prefix-score micro-benchmark
     python tools/sweep_prefix_variants.py attention    # attention micro-benchmark
+    python tools/sweep_prefix_variants.py lazy         # fused per-step prefix kernel
 
 The library under test is selected with E2E_ASR_B200_LIB (e2e-asr-pytorch_b200/_lib.py)."""
 import glob, json, os, subprocess, sys
@@ -17,6 +18,10 @@ shapes = [["--utts", "2620"], ["--utts", "2620", "--plen", "60", "--skip-dead", 
           ["--utts", "600", "--frames", "400", "--ragged", "1", "--plen", "100", "--skip-dead", "1"]]
 if len(sys.argv) > 1 and sys.argv[1] == "attention":
     tool, shapes = "bench_attention.py", [["--ragged", "1"], ["--utts", "2620", "--frames", "824", "--ragged", "1"], ["--utts", "100", "--frames", "824", "--ragged", "1"]]
+elif len(sys.argv) > 1 and sys.argv[1] == "lazy":
+    tool, shapes = "bench_prefix.py", [["--utts", "2620", "--lazy", "1", "--poly", "1", "--plen", "2"], ["--utts", "2620", "--lazy", "1", "--poly", "1", "--plen", "60"],
+                                       ["--utts", "64", "--frames", "825", "--lazy", "1", "--poly", "1", "--plen", "120"],
+                                       ["--utts", "600", "--frames", "400", "--ragged", "1", "--lazy", "1", "--poly", "1", "--plen", "100"]]
 else:
     tool = "bench_prefix.py"
 for lib in sorted(glob.glob(os.path.join(ROOT, "e2e-asr-pytorch_b200", "lib", "variants", "lib_*.so"))):
