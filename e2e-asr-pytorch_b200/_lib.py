@@ -89,6 +89,7 @@ SIGNATURES = {
                                                     c_void_p, c_void_p]),
     "e2e_nbest_pack_ragged": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "e2e_copy_rows_h2d": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "e2e_beam_finalize": (c_int, [c_int, c_int, c_void_p,
                                   c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p,

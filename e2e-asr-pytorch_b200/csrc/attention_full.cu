@@ -62,7 +62,7 @@ struct AttFullParams {
 // measured it at ~4x its HBM floor with 4.  Tuning knob for tools/sweep_prefix_variants.py (the accumulation order,
 // hence the result, does not depend on it).
 #ifndef E2E_AF_CTX_FRAMES
-#define E2E_AF_CTX_FRAMES 4
+#define E2E_AF_CTX_FRAMES 8          // measured (profiles/r02_f_attention_ctx_variants.jsonl): 8 rows in flight 267 vs 362 us on 600 x 824 frames, equal on 2620 x 180; 16: slower
 #endif
 template <int NB, int KP>
 __global__ void __launch_bounds__(kAfThreads, E2E_AF_MINBLOCKS)

@@ -56,11 +56,37 @@ __device__ __forceinline__ void warp_select_topk(int V, int k, int lane, F f, E 
     }
 }
 
+// The same selection over values a lane already holds in registers: lane l owns v = l, l + 32, ... (NV per lane).
+template <int NV, typename E>
+__device__ __forceinline__ void warp_select_topk_cached(const float (&val)[NV], int V, int k, int lane, E emit)
+{
+    float last_v = INFINITY;
+    int last_i = -1;
+    for (int r = 0; r < k; ++r) {
+        float bv = -INFINITY;
+        int bi = INT_MAX;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const int v = lane + 32 * q;
+            const float x = val[q];
+            const bool eligible = v < V && ((x < last_v) || (x == last_v && v > last_i));
+            if (eligible && (x > bv || (x == bv && v < bi))) { bv = x; bi = v; }
+        }
+        warp_argmax(bv, bi);
+        if (bi == INT_MAX) { emit(r, -INFINITY, -1); continue; }
+        emit(r, bv, bi);
+        last_v = bv;
+        last_i = bi;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // (3a) one warp per hypothesis
 // ---------------------------------------------------------------------------------------------
 constexpr int kCandWarps = 4;
 
+// NV > 0 (V <= 32 * NV): the row's log-probs are evaluated once into registers and the top-C rounds work on those.
+template <int NV>
 __global__ void __launch_bounds__(kCandWarps * 32)
 beam_candidates_kernel(const float *__restrict__ att_logits, int ld, int U, int B, int V, int C,
                        const int *__restrict__ n_live, float2 *__restrict__ att_stats, int *__restrict__ cand)
@@ -76,9 +102,19 @@ beam_candidates_kernel(const float *__restrict__ att_logits, int ld, int U, int 
     if (lane == 0) att_stats[n] = make_float2(mx, lse);
     if (C <= 0) return;
     int *out = cand + (long long)n * C;
-    warp_select_topk(
-        V, C, lane, [&](int v) { return logp_from(__ldg(row + v), mx, lse); },
-        [&](int r, float, int idx) { if (lane == 0) out[r] = idx; });
+    if constexpr (NV > 0) {
+        float lp[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const int v = lane + 32 * q;
+            lp[q] = v < V ? logp_from(__ldg(row + v), mx, lse) : -INFINITY;
+        }
+        warp_select_topk_cached<NV>(lp, V, C, lane, [&](int r, float, int idx) { if (lane == 0) out[r] = idx; });
+    } else {
+        warp_select_topk(
+            V, C, lane, [&](int v) { return logp_from(__ldg(row + v), mx, lse); },
+            [&](int r, float, int idx) { if (lane == 0) out[r] = idx; });
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -99,6 +135,10 @@ struct CombineParams {
     int *status;
 };
 
+// NV > 0 (V <= 32 * NV, the character vocabularies): every lane evaluates the attention log-probs and the blended scores of
+// its NV vocabulary entries ONCE, into registers, and the top-k rounds and the <eos> scan work on those; NV == 0: any V,
+// the scores are re-evaluated per round.  Same operations per score either way, hence the same values.
+template <int NV>
 __global__ void __launch_bounds__(1024)
 beam_combine_prune_kernel(const CombineParams p)
 {
@@ -172,20 +212,40 @@ beam_combine_prune_kernel(const CombineParams p)
         };
         float *tv = top_v + w * B;
         int *ti = top_i + w * B;
-        warp_select_topk(V, B, lane, blended, [&](int r, float val, int idx) {
-            if (lane == 0) { tv[r] = val; ti[r] = idx; }
-        });
-        __syncwarp();
-        // ---- <eos> threshold + child creation (Hypothesis.addTopk, decode.py:219-263) ----------
         // The eos test looks at the pure attention log-probs when CTC is on; with CTC off the
         // reference's in-place "+=" of the LM term aliases them.
         const bool alias = (!use_ctc) && use_lm;
-        float best_other = -INFINITY;
-        for (int v = 2 + lane; v < V; v += 32)
-            best_other = fmaxf(best_other, alias ? blended(v) : logp_from(__ldg(att + v), ast.x, ast.y));
-        best_other = warp_max(best_other);
+        float best_other = -INFINITY, eos_lp = -INFINITY;
+        if constexpr (NV > 0) {
+            float bval[NV];
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const int v = lane + 32 * q;
+                bval[q] = -INFINITY;
+                if (v < V) {
+                    bval[q] = blended(v);
+                    const float plain = alias ? bval[q] : logp_from(__ldg(att + v), ast.x, ast.y);
+                    if (v >= 2) best_other = fmaxf(best_other, plain);
+                    if (v == E2E_CTC_EOS) eos_lp = plain;
+                }
+            }
+            warp_select_topk_cached<NV>(bval, V, B, lane, [&](int r, float val, int idx) {
+                if (lane == 0) { tv[r] = val; ti[r] = idx; }
+            });
+            best_other = warp_max(best_other);
+            eos_lp = __shfl_sync(E2E_FULL_MASK, eos_lp, E2E_CTC_EOS & 31);
+        } else {
+            warp_select_topk(V, B, lane, blended, [&](int r, float val, int idx) {
+                if (lane == 0) { tv[r] = val; ti[r] = idx; }
+            });
+            for (int v = 2 + lane; v < V; v += 32)
+                best_other = fmaxf(best_other, alias ? blended(v) : logp_from(__ldg(att + v), ast.x, ast.y));
+            best_other = warp_max(best_other);
+            if (V > 1) eos_lp = alias ? blended(E2E_CTC_EOS) : logp_from(__ldg(att + E2E_CTC_EOS), ast.x, ast.y);
+        }
+        __syncwarp();
+        // ---- <eos> threshold + child creation (Hypothesis.addTopk, decode.py:219-263) ----------
         if (lane == 0) {
-            const float eos_lp = (V > 1) ? (alias ? blended(E2E_CTC_EOS) : logp_from(__ldg(att + E2E_CTC_EOS), ast.x, ast.y)) : -INFINITY;
             const float parent_sum = p.score_sum[n];
             int made = 0;
             for (int r = 0; r < B; ++r) {
@@ -264,16 +324,15 @@ beam_combine_prune_kernel(const CombineParams p)
     for (int i = threadIdx.x; i < B * B; i += blockDim.x) {
         const int b = i / B, k = i - b * B;
         if (b >= live || k >= cnt[b]) continue;
-        int pos = k;
-        for (int bb = 0; bb < b; ++bb) pos += cnt[bb];
+        // list position = (parent, k-th child) order; a child of an earlier parent, or an earlier child of the same parent,
+        // comes first among equal keys
         const float key = c_key[i];
         int rank = 0;
         for (int b2 = 0; b2 < live; ++b2) {
-            int pos2 = 0;
-            for (int bb = 0; bb < b2; ++bb) pos2 += cnt[bb];
-            for (int k2 = 0; k2 < cnt[b2]; ++k2) {
+            const int n2 = cnt[b2];
+            for (int k2 = 0; k2 < n2; ++k2) {
                 const float key2 = c_key[b2 * B + k2];
-                if (key2 > key || (key2 == key && pos2 + k2 < pos)) ++rank;
+                if (key2 > key || (key2 == key && (b2 < b || (b2 == b && k2 < k)))) ++rank;
             }
         }
         if (rank < B) {
@@ -427,7 +486,9 @@ extern "C" int e2e_beam_candidates(const float *att_logits, int ld, int U, int B
     if (!att_logits || !att_stats || (C > 0 && !cand)) return set_error(E2E_ERR_ARG, "e2e_beam_candidates: null pointer");
     if (U <= 0 || B <= 0 || V <= 0 || C < 0 || ld < V || C > V) return set_error(E2E_ERR_ARG, "e2e_beam_candidates: bad size");
     const int N = U * B;
-    beam_candidates_kernel<<<(N + kCandWarps - 1) / kCandWarps, kCandWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+    void (*kern)(const float *, int, int, int, int, int, const int *, float2 *, int *) =
+        V <= 32 ? beam_candidates_kernel<1> : V <= 64 ? beam_candidates_kernel<2> : V <= 128 ? beam_candidates_kernel<4> : beam_candidates_kernel<0>;
+    kern<<<(N + kCandWarps - 1) / kCandWarps, kCandWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
         att_logits, ld, U, B, V, C, n_live, reinterpret_cast<float2 *>(att_stats), cand);
     count_launch();
     return check_launch("e2e_beam_candidates");
@@ -470,12 +531,14 @@ extern "C" int e2e_beam_combine_prune(const float *att_logits, int ld_att, const
     p.fin_count = fin_count; p.fin_step = fin_step; p.fin_parent = fin_parent; p.fin_sum = fin_sum; p.fin_score = fin_score;
     p.fin_cap = fin_cap; p.status = status;
     const size_t smem = combine_smem_bytes(B, p.C);
+    if (n_run <= 0 || n_run > U) n_run = U;
+    void (*kern)(CombineParams) = V <= 32 ? beam_combine_prune_kernel<1> : V <= 64 ? beam_combine_prune_kernel<2>
+                                : V <= 128 ? beam_combine_prune_kernel<4> : beam_combine_prune_kernel<0>;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(beam_combine_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(E2E_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    if (n_run <= 0 || n_run > U) n_run = U;
-    beam_combine_prune_kernel<<<n_run, B * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    kern<<<n_run, B * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
     count_launch();
     return check_launch("e2e_beam_combine_prune");
 }

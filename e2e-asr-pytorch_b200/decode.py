@@ -198,16 +198,19 @@ class BeamDecoder(nn.Module):
             copier = self._copy_stream(dev)
             copier.wait_stream(main)                                   # the memset above
             feat_dev.record_stream(copier)
-            events = []
-            with torch.cuda.stream(copier):
-                for lo in range(0, n_utts, self.ENCODER_CHUNK):
-                    for row in range(lo, min(n_utts, lo + self.ENCODER_CHUNK)):
-                        u = int(order[row])
-                        if lens[u] > 0:
-                            feat_dev[row, :lens[u]].copy_(audio_feature[u, :lens[u]], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(copier)
-                    events.append(ev)
+            n_chunks = (n_utts + self.ENCODER_CHUNK - 1) // self.ENCODER_CHUNK
+            events = [torch.cuda.Event() for _ in range(n_chunks)]
+            for ev in events:
+                ev.record(copier)                      # creates the underlying cudaEvent_t (re-recorded by the copy loop)
+            import ctypes
+            lens32 = np.asarray(lens, dtype=np.int32)
+            order64 = np.ascontiguousarray(order, dtype=np.int64)
+            ev_arr = (ctypes.c_void_p * max(1, n_chunks))(*[ev.cuda_event for ev in events])
+            if audio_feature.dtype != torch.float32 or not audio_feature.is_contiguous():
+                raise ValueError("decode_batch_from_host: features must be a contiguous fp32 tensor")
+            L.check(L.load().e2e_copy_rows_h2d(audio_feature.data_ptr(), feat_dev.data_ptr(), int(audio_feature.shape[1] * audio_feature.shape[2]),
+                                              int(audio_feature.shape[2]), lens32.ctypes.data, order64.ctypes.data, n_utts,
+                                              self.ENCODER_CHUNK, ev_arr, copier.cuda_stream))
             self.last_h2d_bytes = sum(lens) * audio_feature.shape[2] * 4 + feature_len.numel() * feature_len.element_size()
             enc_mod = self.asr.encoder
 

@@ -271,10 +271,25 @@ def ragged_size(shards, lengths, beam, max_len_ratio):
     return max([ragged_layout(ids, lengths, beam, max_len_ratio)[1] for ids in shards] + [1])
 
 
+_PINNED = {}
+
+
+def _pinned(shape, dtype):
+    """One persistent pinned read-back buffer per (shape, dtype): allocating page-locked memory costs milliseconds, so the
+    buffer is kept; a gather overwrites what the previous one returned."""
+    key = (tuple(shape), dtype)
+    buf = _PINNED.get(key)
+    if buf is None:
+        buf = torch.empty(shape, dtype=dtype, pin_memory=True)
+        _PINNED.clear()
+        _PINNED[key] = buf
+    return buf
+
+
 def gather_nbest(local_buf, device=None, marks=None):
     """The one collective of the sharded decode: all-gather of the packed buffers (same shape on every rank).
     Returns the concatenation of all ranks' buffers on the host.  A CUDA ``local_buf`` (RaggedPacker) is gathered where
-    it lies and read back ONCE into pinned host memory; a CPU buffer (gloo tests, legacy CPU packing) is sent as it is."""
+    it lies and read back ONCE into a persistent pinned host buffer (overwritten by the next gather); a CPU buffer (gloo tests, legacy CPU packing) is sent as it is."""
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     if local_buf.is_cuda:
         recv = local_buf
@@ -284,7 +299,7 @@ def gather_nbest(local_buf, device=None, marks=None):
             dist.all_gather_into_tensor(recv, local_buf.contiguous())
         if marks is not None:
             marks[0].record()                                                  # (CUDA events: after the gather, after the read-back)
-        host = torch.empty(recv.shape, dtype=recv.dtype, pin_memory=True)     # the caching host allocator reuses the block
+        host = _pinned(recv.shape, recv.dtype)
         host.copy_(recv, non_blocking=True)
         if marks is not None:
             marks[1].record()

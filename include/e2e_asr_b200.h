@@ -341,6 +341,14 @@ int e2e_conv_bias_relu_mask_pool_scaled(const float *y_nhwc, const float *bias, 
                                         float *out_nhwc, const unsigned *amax_in, float inv_w_scale, unsigned *amax_out,
                                         void *stream);
 
+/* Host -> device copy of the VALID frames of n rows of a zero-padded [U][Lmax][D] fp32 feature tensor in pinned host memory
+ * (the `.to(device)` of bin/test_asr.py:161-163, without the padding): device row r receives the first lens_host[order_host[r]]
+ * frames of host row order_host[r]; one asynchronous copy per row on `stream`; after every `chunk` rows events[r / chunk]
+ * (cudaEvent_t, caller-created; may be NULL) is recorded.  row_pitch = Lmax * D floats.  lens_host / order_host / events are
+ * HOST arrays. */
+int e2e_copy_rows_h2d(const float *host, float *dev, long long row_pitch, int D, const int *lens_host,
+                      const long long *order_host, int n, int chunk, void *const *events, void *stream);
+
 /* Number of kernel launches issued through this library by the calling process
  * (for bench.py's gpu_launches claim). */
 long long e2e_launch_count(void);
