@@ -56,6 +56,43 @@ __device__ __forceinline__ void warp_select_topk(int V, int k, int lane, F f, E 
     }
 }
 
+// The same selection for WIDE rows (the 10k subword vocabulary) in ONE pass over the row: every lane streams its entries
+// v = lane, lane + 32, ... through visit(v) -> value and keeps its own k best in a sorted list in shared memory
+// (lst_v / lst_i: [k][32], this lane's column; later equal values stay behind earlier ones), then the lists' heads are
+// merged by k warp arg-max rounds (ties to the lower index).  Every entry is evaluated once instead of once per round.
+template <typename F, typename E>
+__device__ __forceinline__ void warp_select_topk_stream(int V, int k, int lane, F visit, E emit, float *lst_v, int *lst_i)
+{
+    for (int r = 0; r < k; ++r) { lst_v[r * 32 + lane] = -INFINITY; lst_i[r * 32 + lane] = INT_MAX; }
+    float worst = -INFINITY;                               // this lane's k-th best so far
+    int filled = 0;
+    for (int v = lane; v < V; v += 32) {
+        const float x = visit(v);
+        if (filled < k || x > worst) {
+            int pos = filled < k ? filled : k - 1;
+            while (pos > 0 && lst_v[(pos - 1) * 32 + lane] < x) {
+                lst_v[pos * 32 + lane] = lst_v[(pos - 1) * 32 + lane];
+                lst_i[pos * 32 + lane] = lst_i[(pos - 1) * 32 + lane];
+                --pos;
+            }
+            lst_v[pos * 32 + lane] = x;
+            lst_i[pos * 32 + lane] = v;
+            if (filled < k) ++filled;
+            if (filled == k) worst = lst_v[(k - 1) * 32 + lane];
+        }
+    }
+    int head = 0;                                          // next unread entry of this lane's list
+    for (int r = 0; r < k; ++r) {
+        float bv = head < filled ? lst_v[head * 32 + lane] : -INFINITY;
+        int bi = head < filled ? lst_i[head * 32 + lane] : INT_MAX;
+        const int mine = bi;
+        warp_argmax(bv, bi);
+        if (bi == INT_MAX) { emit(r, -INFINITY, -1); continue; }
+        emit(r, bv, bi);
+        if (mine == bi) ++head;
+    }
+}
+
 // The same selection over values a lane already holds in registers: lane l owns v = l, l + 32, ... (NV per lane).
 template <int NV, typename E>
 __device__ __forceinline__ void warp_select_topk_cached(const float (&val)[NV], int V, int k, int lane, E emit)
@@ -111,9 +148,12 @@ beam_candidates_kernel(const float *__restrict__ att_logits, int ld, int U, int 
         }
         warp_select_topk_cached<NV>(lp, V, C, lane, [&](int r, float, int idx) { if (lane == 0) out[r] = idx; });
     } else {
-        warp_select_topk(
+        extern __shared__ __align__(16) unsigned char cand_smem[];          // [warps][C][32] values | [warps][C][32] ids
+        float *lv = reinterpret_cast<float *>(cand_smem) + (size_t)(threadIdx.x >> 5) * C * 32;
+        int *li = reinterpret_cast<int *>(cand_smem) + (size_t)kCandWarps * C * 32 + (size_t)(threadIdx.x >> 5) * C * 32;
+        warp_select_topk_stream(
             V, C, lane, [&](int v) { return logp_from(__ldg(row + v), mx, lse); },
-            [&](int r, float, int idx) { if (lane == 0) out[r] = idx; });
+            [&](int r, float, int idx) { if (lane == 0) out[r] = idx; }, lv, li);
     }
 }
 
@@ -174,6 +214,11 @@ beam_combine_prune_kernel(const CombineParams p)
     float *top_v = w_delta + B * (C > 0 ? C : 1);              // [B][B] winners per parent
     int *top_i = reinterpret_cast<int *>(top_v + B * B);
     int *par_tok = top_i + B * B;                              // [B] the parents' own last tokens
+    // wide rows only (NV == 0): per-warp streaming top-B lists [B][B][32] x (value, id) and candidate bitmaps [B][ceil(V/32)]
+    float *stream_v = reinterpret_cast<float *>(par_tok + B);
+    int *stream_i = reinterpret_cast<int *>(stream_v + (NV == 0 ? (size_t)B * B * 32 : 0));
+    const int bit_words = (V + 31) >> 5;
+    unsigned *cand_bits = reinterpret_cast<unsigned *>(stream_i + (NV == 0 ? (size_t)B * B * 32 : 0));
 
     if (threadIdx.x < B) {
         cnt[threadIdx.x] = 0; term[threadIdx.x] = 0;
@@ -234,7 +279,9 @@ beam_combine_prune_kernel(const CombineParams p)
             });
             best_other = warp_max(best_other);
             eos_lp = __shfl_sync(E2E_FULL_MASK, eos_lp, E2E_CTC_EOS & 31);
-        } else {
+        } else if constexpr (NV < 0) {
+            // any width, no extra shared memory: the scores are re-evaluated in every top-k round (beam sizes whose streaming lists
+            // would not fit)
             warp_select_topk(V, B, lane, blended, [&](int r, float val, int idx) {
                 if (lane == 0) { tv[r] = val; ti[r] = idx; }
             });
@@ -242,6 +289,39 @@ beam_combine_prune_kernel(const CombineParams p)
                 best_other = fmaxf(best_other, alias ? blended(v) : logp_from(__ldg(att + v), ast.x, ast.y));
             best_other = warp_max(best_other);
             if (V > 1) eos_lp = alias ? blended(E2E_CTC_EOS) : logp_from(__ldg(att + E2E_CTC_EOS), ast.x, ast.y);
+        } else {
+            // wide rows: ONE pass — every entry is blended once, feeds this lane's top-B list and the <eos> scan; a bitmap of the
+            // candidate ids replaces the C compares per entry
+            float *lv = stream_v + (size_t)w * B * 32;
+            int *li = stream_i + (size_t)w * B * 32;
+            unsigned *bits = cand_bits + (size_t)w * bit_words;
+            for (int i = lane; i < bit_words; i += 32) bits[i] = 0u;
+            __syncwarp();
+            if (use_ctc)
+                for (int j = lane; j < C; j += 32) atomicOr(bits + (mycand[j] >> 5), 1u << (mycand[j] & 31));
+            __syncwarp();
+            auto visit = [&](int v) -> float {
+                const float plain_att = logp_from(__ldg(att + v), ast.x, ast.y);
+                float cur = plain_att;
+                if (use_ctc) {
+                    float spread = E2E_DEC_LOG_ZERO;
+                    if ((bits[v >> 5] >> (v & 31)) & 1u)
+                        for (int j = 0; j < C; ++j)
+                            if (mycand[j] == v) { spread = mydelta[j]; break; }
+                    cur = __fadd_rn(__fmul_rn(p.w_att, cur), __fmul_rn(p.w_ctc, spread));
+                    if (v == 0) cur = E2E_DEC_LOG_ZERO;
+                }
+                if (use_lm) cur = __fadd_rn(cur, __fmul_rn(p.w_lm, logp_from(__ldg(lm + v), lmx, llse)));
+                const float plain = alias ? cur : plain_att;
+                if (v >= 2) best_other = fmaxf(best_other, plain);
+                if (v == E2E_CTC_EOS) eos_lp = plain;
+                return cur;
+            };
+            warp_select_topk_stream(V, B, lane, visit, [&](int r, float val, int idx) {
+                if (lane == 0) { tv[r] = val; ti[r] = idx; }
+            }, lv, li);
+            best_other = warp_max(best_other);
+            eos_lp = __shfl_sync(E2E_FULL_MASK, eos_lp, E2E_CTC_EOS & 31);
         }
         __syncwarp();
         // ---- <eos> threshold + child creation (Hypothesis.addTopk, decode.py:219-263) ----------
@@ -364,10 +444,12 @@ beam_combine_prune_kernel(const CombineParams p)
     }
 }
 
-static size_t combine_smem_bytes(int B, int C)
+static size_t combine_smem_bytes(int B, int C, int V, bool stream)
 {
     const int Cc = C > 0 ? C : 1;
-    return (size_t)(6 * B * B + 4 * B + 2 * B * Cc + 2 * B * B) * 4 + 16;
+    size_t words = (size_t)(6 * B * B + 4 * B + 2 * B * Cc + 2 * B * B);
+    if (stream) words += (size_t)2 * B * B * 32 + (size_t)B * ((V + 31) / 32);        // streaming lists + candidate bitmaps
+    return words * 4 + 16;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -488,7 +570,13 @@ extern "C" int e2e_beam_candidates(const float *att_logits, int ld, int U, int B
     const int N = U * B;
     void (*kern)(const float *, int, int, int, int, int, const int *, float2 *, int *) =
         V <= 32 ? beam_candidates_kernel<1> : V <= 64 ? beam_candidates_kernel<2> : V <= 128 ? beam_candidates_kernel<4> : beam_candidates_kernel<0>;
-    kern<<<(N + kCandWarps - 1) / kCandWarps, kCandWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+    const size_t smem = V > 128 ? (size_t)kCandWarps * C * 32 * 8 : 0;      // per-lane top-C lists of the streaming selection
+    if (smem > 48 * 1024) {
+        if (smem > 200 * 1024) return set_error(E2E_ERR_UNSUPPORTED, "e2e_beam_candidates: C too large");
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(E2E_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    kern<<<(N + kCandWarps - 1) / kCandWarps, kCandWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
         att_logits, ld, U, B, V, C, n_live, reinterpret_cast<float2 *>(att_stats), cand);
     count_launch();
     return check_launch("e2e_beam_candidates");
@@ -530,10 +618,12 @@ extern "C" int e2e_beam_combine_prune(const float *att_logits, int ld_att, const
     p.parent_row = parent_row; p.last_tok64 = last_tok64; p.parent_tok = parent_tok;
     p.fin_count = fin_count; p.fin_step = fin_step; p.fin_parent = fin_parent; p.fin_sum = fin_sum; p.fin_score = fin_score;
     p.fin_cap = fin_cap; p.status = status;
-    const size_t smem = combine_smem_bytes(B, p.C);
+    bool stream_sel = V > 128;
+    if (stream_sel && combine_smem_bytes(B, p.C, V, true) > 160 * 1024) stream_sel = false;      // multi-pass selection instead
+    const size_t smem = combine_smem_bytes(B, p.C, V, stream_sel);
     if (n_run <= 0 || n_run > U) n_run = U;
     void (*kern)(CombineParams) = V <= 32 ? beam_combine_prune_kernel<1> : V <= 64 ? beam_combine_prune_kernel<2>
-                                : V <= 128 ? beam_combine_prune_kernel<4> : beam_combine_prune_kernel<0>;
+                                : V <= 128 ? beam_combine_prune_kernel<4> : stream_sel ? beam_combine_prune_kernel<0> : beam_combine_prune_kernel<-1>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(E2E_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -171,11 +171,15 @@ def _beam_from(tokens, scores, ctc_prob=0.0):
                    None, None, None, None, np.float32(ctc_prob))
 
 
-@pytest.mark.parametrize("case", ["equal_keys", "few_live", "eos_closes", "eos_boundary_not_closed", "min_len_blocks", "lm_alias", "all_three"])
-def test_beam_combine_prune_hand_made_states(cuda, case):
+@pytest.mark.parametrize("case,vocab", [("equal_keys", 31), ("few_live", 31), ("eos_closes", 31), ("eos_boundary_not_closed", 31),
+                                        ("min_len_blocks", 31), ("lm_alias", 31), ("all_three", 31),
+                                        # 64 / 128-wide rows: 2 / 4 cached entries per lane; wider: the one-pass streaming selection
+                                        ("all_three", 50), ("equal_keys", 100), ("all_three", 300), ("eos_closes", 300), ("lm_alias", 10000),
+                                        ("all_three", 10000), ("equal_keys", 10000)])
+def test_beam_combine_prune_hand_made_states(cuda, case, vocab):
     ops = _ops()
-    rng = np.random.default_rng(sum(map(ord, case)))
-    vocab, beam, step = 31, 4, 3
+    rng = np.random.default_rng(sum(map(ord, case)) + vocab)
+    beam, step = 4, 3
     ctc_w, lm_w, min_len = 0.0, 0.0, 0
     # three tokens per parent; fp32-exact scores so that equal sums ARE equal
     parents = [_beam_from([5, 6, 7], [-0.25, -0.25, -0.5]), _beam_from([5, 6, 8], [-0.5, -0.25, -0.25]),
