@@ -404,6 +404,7 @@ template <bool kGather, bool kFixed, int kT, bool kBig>
 static LazyKernel pick_math(int math)
 {
     if (math == kMathPoly) return prefix_lazy_kernel<kGather, kMathPoly, kFixed, kT, kBig>;
+    if (math == kMathPolyEstrin) return prefix_lazy_kernel<kGather, kMathPolyEstrin, kFixed, kT, kBig>;
     return prefix_lazy_kernel<kGather, kMathLut, kFixed, kT, kBig>;
 }
 
@@ -448,7 +449,14 @@ extern "C" int e2e_ctc_prefix_step(const float *x, int Tmax, int U, int Vp, int 
     const bool big = threads > 160;
     const bool gather = Vp > kLazyMaxRowFloats;
     const bool fixed = !gather && Vp == 32 && B == 8 && C == 12;     // char vocabulary, beam 8 (BASELINE cfg2)
-    const int math = (flags & E2E_PREFIX_POLY_MATH) ? kMathPoly : kMathLut;
+    // Polynomial log-add-exp: Horner (14 instructions, 10 dependent after the MUFU) for machine-filling launches, which are
+    // bound by instruction issue; the pairwise (Estrin) evaluation (17 instructions, 6 dependent) for launches that cannot
+    // fill the machine and last as long as the longest utterance's dependent chain.  E2E_PREFIX_POLY_ESTRIN forces the latter.
+    static const int estrin_below = []() {
+        const char *e = getenv("E2E_LAZY_ESTRIN_BELOW");             // tuning knob: utterances below which Estrin is used
+        return e ? atoi(e) : 1000;
+    }();
+    const int math = (flags & E2E_PREFIX_POLY_MATH) ? (((flags & E2E_PREFIX_POLY_ESTRIN) || n_run < estrin_below) ? kMathPolyEstrin : kMathPoly) : kMathLut;
     // 16-frame tiles for machine-filling launches (more CTAs per SM), 32-frame tiles for the tail (fewer barriers per chain)
     static const int small_from = []() {
         const char *e = getenv("E2E_LAZY_SMALL_TILE_FROM");          // tuning knob: utterances from which the 16-frame tile is used
