@@ -11,8 +11,8 @@ crosses GPUs.  The buffer is RAGGED (every rank derives the same layout from the
 length list: no ids travel, nothing is padded to the set's longest utterance; ~4.5x
 smaller than rectangular rows for a dev-clean-like set) and is packed ON THE DEVICE
 from the finalize kernel's outputs (RaggedPacker -> e2e_nbest_pack_ragged), gathered
-where it lies and read back once into pinned host memory.  pack_nbest (rectangular)
-and pack_nbest_ragged (CPU) remain for the gloo tests and as cross-checks.
+where it lies and read back once into pinned host memory.  pack_nbest_ragged (the same
+layout packed on the CPU) remains for the gloo tests and as the cross-check of the kernel.
 """
 import numpy as np
 import torch
@@ -83,50 +83,10 @@ def make_batches(indices, lengths, max_utts=512, max_padded_frames=None, max_byt
     return batches
 
 
-# ---- packed N-best buffer -----------------------------------------------------------------------
-# row = [utt_id, n, len_0..len_{B-1}, avgbits_0..avgbits_{B-1}, tok[B*cap], scorebits[B*cap]]  (int32)
 def row_width(beam, cap):
+    """int32 words per utterance of a RECTANGULAR buffer padded to the set's longest utterance (round 1's format; kept as
+    the yardstick the ragged layout is compared with)."""
     return 2 + 2 * beam + 2 * beam * cap
-
-
-def pack_nbest(utt_ids, tok, sc, ln, avg, n, cap, rows):
-    """CPU int32 [rows, row_width]; unused rows have utt_id = -1."""
-    u, beam, have = tok.shape
-    buf = torch.zeros((rows, row_width(beam, cap)), dtype=torch.int32)
-    buf[:, 0] = -1
-    if u == 0:
-        return buf
-    buf[:u, 0] = torch.as_tensor(np.asarray(utt_ids), dtype=torch.int32)
-    buf[:u, 1] = n.to(torch.int32)
-    buf[:u, 2:2 + beam] = ln.to(torch.int32)
-    buf[:u, 2 + beam:2 + 2 * beam] = avg.to(torch.float32).contiguous().view(torch.int32)
-    w = min(cap, have)
-    t = torch.zeros((u, beam, cap), dtype=torch.int32)
-    s = torch.zeros((u, beam, cap), dtype=torch.float32)
-    t[:, :, :w], s[:, :, :w] = tok[:, :, :w], sc[:, :, :w]
-    o = 2 + 2 * beam
-    buf[:u, o:o + beam * cap] = t.view(u, -1)
-    buf[:u, o + beam * cap:] = s.view(u, -1).view(torch.int32)
-    return buf
-
-
-def unpack_nbest(buf, beam, cap, n_total):
-    """Inverse of pack_nbest over the concatenation of all ranks' buffers; returns arrays
-    indexed by global utterance id."""
-    buf = buf.cpu()
-    ids = buf[:, 0].long()
-    ok = ids >= 0
-    rows, ids = buf[ok], ids[ok]
-    assert len(ids) == n_total and len(torch.unique(ids)) == n_total, "N-best gather lost or duplicated utterances"
-    order = torch.argsort(ids)
-    rows = rows[order]
-    o = 2 + 2 * beam
-    n = rows[:, 1].clone()
-    ln = rows[:, 2:2 + beam].clone()
-    avg = rows[:, 2 + beam:o].contiguous().view(torch.float32).clone()
-    tok = rows[:, o:o + beam * cap].reshape(n_total, beam, cap).clone()
-    sc = rows[:, o + beam * cap:].contiguous().view(torch.float32).reshape(n_total, beam, cap).clone()
-    return tok, sc, ln, avg, n
 
 
 # ---- ragged N-best buffer ------------------------------------------------------------------------
