@@ -86,3 +86,37 @@ def test_reference_checkpoint_layout_loads_into_product_model():
     lm_a = synth.build_lm(31).state_dict()
     lm_b = ref.RNNLM(31, **copy.deepcopy(synth.LM_MODEL_CFG)).state_dict()
     assert list(lm_a.keys()) == list(lm_b.keys()) and all(lm_a[k].shape == lm_b[k].shape for k in lm_a)
+
+
+def test_staged_reference_bytecode_equals_the_live_tree():
+    """oracle/_ref (the reference's decode path byte-compiled by oracle/ref_stage.py — what travels to the GPU box for
+    bench.py's CPU arm and the drop-in test) behaves like the live source tree: same N-best, same scores, through
+    bin/test_asr.py::beam_decode.  Each variant runs in its own interpreter (one import of `src.*` per process)."""
+    import json, os, subprocess, sys
+    from oracle import ref_stage
+    ref_stage.stage()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prog = r'''
+import sys, json, copy, torch
+sys.path.insert(0, %r)
+from oracle import refload
+from e2e_asr_pytorch_b200 import synth
+staged = sys.argv[1] == "staged"
+ref = refload.load(staged=staged)
+ta = refload.load_test_asr(staged=staged)
+mine = synth.build_asr(31, synth.TINY_ASR_CFG, seed=0, peak=4.0)
+rasr = ref.ASR(synth.FEAT_DIM, 31, True, **copy.deepcopy(synth.TINY_ASR_CFG)).eval()
+rasr.load_state_dict(mine.state_dict())
+dec = ref.BeamDecoder(rasr, None, 4, 0.01, 0.2, ctc_weight=0.5)
+name, hyps, _ = ta.beam_decode((["u"], synth.utterance(7, 92)[None], torch.LongTensor([92]), torch.zeros(1, 1, dtype=torch.long)), dec, "cpu")
+with torch.no_grad():
+    sc = [float(h.avgScore()) for h in dec(synth.utterance(7, 92)[None], torch.LongTensor([92]))]
+print(json.dumps({"kind": ref.kind, "hyps": hyps, "scores": sc}))
+''' % root
+    outs = {}
+    for kind in ("live", "staged"):
+        r = subprocess.run([sys.executable, "-c", prog, kind], capture_output=True, text=True, timeout=300, cwd=root)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[kind] = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert outs["live"]["kind"] == "live" and outs["staged"]["kind"] == "staged"
+    assert outs["live"]["hyps"] == outs["staged"]["hyps"] and outs["live"]["scores"] == outs["staged"]["scores"]
