@@ -31,6 +31,7 @@ SIGNATURES = {
     "e2e_abi_version": (c_int, []),
     "e2e_padded_vocab": (c_int, [c_int]),
     "e2e_launch_count": (ctypes.c_longlong, []),
+    "e2e_add_launch_count": (None, [ctypes.c_longlong]),
     "e2e_ctc_log_softmax": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "e2e_ctc_init_state": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "e2e_ctc_prefix_score": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p,

@@ -34,6 +34,8 @@ extern "C" const char *e2e_last_error(void) { return e2e::g_err; }
 extern "C" int e2e_abi_version(void) { return E2E_ABI_VERSION; }
 extern "C" int e2e_padded_vocab(int V) { return V <= 0 ? 0 : (V + 3) & ~3; }
 extern "C" long long e2e_launch_count(void) { return e2e::g_launches.load(std::memory_order_relaxed); }
+// Kernels of this library that ran as nodes of a replayed CUDA graph (captured launches are counted at capture time only).
+extern "C" void e2e_add_launch_count(long long n) { e2e::count_launch((int)n); }
 
 // Host -> device copy of the valid frames of n rows of a zero-padded [U][Lmax][D] fp32 feature tensor (pinned host memory):
 // row r of the DEVICE tensor receives the first lens[order[r]] frames of HOST row order[r], one cudaMemcpyAsync per row on

@@ -139,6 +139,9 @@ class BeamDecoder(nn.Module):
         # the device from the running maximum of every layer's input, csrc/conv_split.cu)
         self.vgg_split = os.environ.get("E2E_VGG_SPLIT", "bf16x3")
         self.fused_attention = True     # hand-written location-aware attention kernel (csrc/attention_full.cu)
+        # replay the LSTM stacks of a decode step from CUDA graphs when few utterances are live (stepper._FusedLstm): the tail of a
+        # decode is bound by the host's launch rate
+        self.step_graphs = os.environ.get("E2E_STEP_GRAPHS", "1") != "0"
         self._stepper = None            # (device, split_gemm, stepper): weights are split once per device
         self.profile_prefix = False     # bench.py: CUDA-event pair around every prefix-score launch
         self.prefix_events = []         # (start, end, cand_frames [SURVEY §8d formula], cand_frames actually computed)
@@ -284,10 +287,11 @@ class BeamDecoder(nn.Module):
 
         with _Fp32Math():
             mark("start", True)
-            knobs = (self.split_gemm, self.fused_attention, self.lm_split, self.vgg_split)
+            knobs = (self.split_gemm, self.fused_attention, self.lm_split, self.vgg_split, self.step_graphs)
             if self._stepper is None or self._stepper[0] != dev or self._stepper[1] != knobs:
                 self._stepper = (dev, knobs, BatchedStepper(self.asr, self.lm if self.apply_lm else None,
-                                                            self.split_gemm, self.fused_attention, self.lm_split, self.vgg_split))
+                                                            self.split_gemm, self.fused_attention, self.lm_split, self.vgg_split,
+                                                            self.step_graphs))
             stepper = self._stepper[2]
             stepper.mark = mark
             enc, enc_len = stepper.encode(audio_feature, feature_len.to(dev))

@@ -440,3 +440,7 @@ def conv_bias_relu_mask_pool(y_nhwc, bias, valid_rows, amax_in=None, inv_w_scale
 
 def launch_count():
     return int(L.load().e2e_launch_count())
+
+
+def add_launch_count(n):
+    L.load().e2e_add_launch_count(int(n))

@@ -212,14 +212,37 @@ class _FusedLstm:
                 self.k_in.append(w_ih.shape[1])
         self.cur = 0
 
+    # Rows (live utterances x beam) up to which a step is REPLAYED FROM A CUDA GRAPH: below ~500 live utterances a decode step
+    # is bound by the host's launch rate (tools/profile_tail.py: the last 360 steps of the bench take 215 ms of host time for
+    # 215 ms of device time), and the LSTM stacks are 23 of a step's ~48 launches.  Row counts are rounded up to a ladder so
+    # that a graph is reused while the live count shrinks; the padding rows belong to finished utterances and are never read.
+    GRAPH_MAX_ROWS = 4096
+    GRAPH_LADDER = (64, 128, 256, 384, 512, 768, 1024, 1536, 2048, 2560, 3072, 3584, 4096)
+    use_graphs = False
+
     def start(self, n, device):
         d = self.dim
+        if getattr(self, "cap", 0) >= n and getattr(self, "device", None) == device:
+            # same buffers as the last decode (and the graphs captured over them): only the initial states are reset
+            for l in range(self.layers):
+                self.h[0][l][:n].zero_()
+                self.c[0][l][:n].zero_()
+            self.idx = self.idx_buf[:n]
+            self.idx_buf.copy_(self._arange)
+            self.cur = 0
+            return
+        self.cap, self.device, self.graphs = n, device, {}
         self.h = [[torch.zeros(n, d, device=device) for _ in range(self.layers)] for _ in range(2)]
         self.c = [[torch.zeros(n, d, device=device) for _ in range(self.layers)] for _ in range(2)]
         pieces, a_dtype = (2, torch.float16) if self.f16 else (3, torch.bfloat16)
         self.a = [torch.empty(n, pieces * (self.k_in[l] + d), dtype=a_dtype, device=device) for l in range(self.layers)]
         self.gates = torch.empty(n, 4 * d, device=device)          # GEMM accumulator, reused by every layer
-        self.idx = torch.arange(n, device=device)
+        # static homes of a step's varying inputs (what a captured graph reads): parent rows, tokens, layer-0 input
+        self._arange = torch.arange(n, device=device)
+        self.idx_buf = self._arange.clone()
+        self.tok_buf = torch.zeros(n, dtype=torch.int64, device=device)
+        self.x0_buf = torch.zeros(n, self.k_in[0], device=device) if self.k_in[0] > 0 else None
+        self.idx = self.idx_buf[:n]
         self.cur = 0
         from . import ops
         vec = d % 4 == 0 and all(k % 4 == 0 for k in self.k_in)
@@ -232,11 +255,55 @@ class _FusedLstm:
         hs = [h.index_select(0, self.idx[:n]) for h in self.h[self.cur]]
         return hs[0] if len(hs) == 1 else torch.cat(hs, dim=1)
 
+    def x0_home(self, n):
+        """Where the caller may build the layer-0 input of the next step directly (the static buffer a graph reads)."""
+        return self.x0_buf[:n] if (self.x0_buf is not None and self._graph_rows(n)) else None
+
+    def _graph_rows(self, n):
+        if not self.use_graphs or n > self.GRAPH_MAX_ROWS or torch.cuda.is_current_stream_capturing():
+            return 0
+        for r in self.GRAPH_LADDER:
+            if n <= r:
+                return min(r, self.cap)
+        return 0
+
     def step(self, n, x0=None, tok=None):
         """Advance rows [:n]; x0 [n, in] fp32 (or tok [n] for a tabled layer 0) -> top hidden [n, D]."""
+        nr = self._graph_rows(n)
+        if nr == 0:
+            return self._step_eager(n, x0, tok, self.idx)
+        # stage the step's varying inputs in their static buffers, then replay the graph of (padded rows, ping-pong parity)
+        from . import ops
+        if self.idx.data_ptr() != self.idx_buf.data_ptr():
+            self.idx_buf[:n].copy_(self.idx[:n])
+        if tok is not None and self.table0 is not None:
+            self.tok_buf[:n].copy_(tok[:n])
+        if x0 is not None and x0.data_ptr() != self.x0_buf.data_ptr():
+            self.x0_buf[:n].copy_(x0)
+        key = (nr, self.cur)
+        g = self.graphs.get(key)
+        if g is None:
+            cur = self.cur
+            body = lambda: self._step_eager(nr, self.x0_buf[:nr] if self.x0_buf is not None else None, self.tok_buf[:nr], self.idx_buf)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):            # once for real on a side stream (library handles / workspaces), as torch asks
+                body()
+            torch.cuda.current_stream().wait_stream(side)
+            self.cur = cur
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self.cur = cur
+            self.graphs[key] = g
+        g.replay()
+        ops.add_launch_count(1 + (1 if self.k_in[0] > 0 else 0) + self.layers)      # the library's own kernels inside the graph
+        self.cur = 1 - self.cur
+        return self.h[self.cur][self.layers - 1][:n]
+
+    def _step_eager(self, n, x0, tok, idx):
         from . import ops
         cur, new, d = self.cur, 1 - self.cur, self.dim
-        idx = self.idx
         if self.plans[cur] is not None:                                # recurrent halves of all A operands, one launch
             self.plans[cur].run(idx, n)
         else:
@@ -267,7 +334,7 @@ class _FusedLstm:
 
 
 class BatchedStepper:
-    def __init__(self, asr, lm=None, split_gemm=False, fused_attention=False, lm_split="bf16x3", vgg_split="bf16x3"):
+    def __init__(self, asr, lm=None, split_gemm=False, fused_attention=False, lm_split="bf16x3", vgg_split="bf16x3", step_graphs=False):
         att = asr.attention
         if att.num_head != 1:
             raise NotImplementedError("multi-head attention is not supported by the batched beam search")
@@ -288,6 +355,9 @@ class BatchedStepper:
             return _Rnn(rnn, split_gemm, table)
         self.dec = make(asr.decoder.layers)                  # speller inputs (embedding, context) have no fixed range: bf16x3
         self.lm_rnn = make(lm.rnn, lm.emb.weight.detach(), lm_split) if lm is not None else None
+        for stack in (self.dec, self.lm_rnn):
+            if isinstance(stack, _FusedLstm):
+                stack.use_graphs = bool(step_graphs)
         self.mark = lambda name: None            # profiling hook (decode.py sets it)
         self.fused_attention = False
         if fused_attention and self.mode == "loc":
@@ -416,10 +486,13 @@ class BatchedStepper:
             attn = torch.softmax(score, dim=-1)                                        # [k,B,T]
             context = torch.bmm(attn, self.value[:k]).view(n, -1)                      # module.py:1114
         self.mark("step_attention")
-        dec_in = torch.cat([asr.pre_embed(prev_tok), context], dim=-1)             # decode.py:114-115
         if self.dec_fused:
+            home = self.dec.x0_home(n)                                             # decode.py:114-115
+            dec_in = torch.cat([asr.pre_embed(prev_tok), context], dim=-1, out=home) if home is not None else \
+                torch.cat([asr.pre_embed(prev_tok), context], dim=-1)
             top = self.dec.step(n, x0=dec_in)
         else:
+            dec_in = torch.cat([asr.pre_embed(prev_tok), context], dim=-1)
             top, self._new_dec = self.dec.step(dec_in, self.dec_state, n)
         att_logits = asr.decoder.char_trans(top)                                   # asr.py:265
         self._new_att = attn.view(n, t) if self.mode == "loc" else None

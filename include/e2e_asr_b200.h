@@ -352,6 +352,8 @@ int e2e_copy_rows_h2d(const float *host, float *dev, long long row_pitch, int D,
 /* Number of kernel launches issued through this library by the calling process
  * (for bench.py's gpu_launches claim). */
 long long e2e_launch_count(void);
+/* Adds n to that count: the library's kernels that ran as nodes of a CUDA graph the caller replayed. */
+void e2e_add_launch_count(long long n);
 
 #ifdef __cplusplus
 }
