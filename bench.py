@@ -10,11 +10,17 @@ N GPUs decode N x 2620 utterances, sharded by utterance, one all-gather of the N
 A "step" is one pass of the hot path over that whole set.
 
 Prints ONE JSON line (rank 0).  ``value`` = utterances/s with the features already resident in
-HBM; ``e2e`` = the same through BeamDecoder.decode_batch with pinned HOST features (H2D inside
-the timed region, N-best read back to the host).  ``roofline`` describes the prefix-score
-kernel (the dominant hand-written kernel), timed live with CUDA events around every launch.
-``--impl reference`` times the CPU implementation (oracle port of the reference — the reference
-itself is Python under /root/reference and cannot travel to the GPU box) on the host cores.
+HBM; ``e2e`` = the same through BeamDecoder.decode_batch_from_host with pinned HOST features (the
+valid frames copied inside the timed region, pipelined under the encoder; the ragged N-best packed
+on the device, gathered and read back to pinned host memory).  ``roofline`` describes the fused
+prefix-score step kernel, timed live with CUDA events around every launch; ``phases_ms`` is the
+per-phase breakdown of a pass (max over ranks); ``nbest_parity`` compares the run's own N-best of
+the 16 bench-set utterances in tests/golden/beam_nbest_fullsize.npz with the reference's;
+``sharded_equals_single`` (N > 1) is the bit-for-bit check of the gathered result against rank 0's
+own decode of the last rank's shard.
+``--impl reference`` times the UNMODIFIED reference on the host cores: its decode path byte-compiled
+into oracle/_ref by __graft_entry__.build() (oracle/ref_stage.py), driven through
+bin/test_asr.py::beam_decode and joblib.Parallel on a length-stratified sample of the same set.
 """
 import argparse
 import json
