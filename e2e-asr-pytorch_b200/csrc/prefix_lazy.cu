@@ -320,13 +320,26 @@ prefix_lazy_kernel(const LazyParams p, const __grid_constant__ CUtensorMap tmap)
                     s0_prev = s0n;
                     xl_prev = xl;
                 };
-                for (; tt + 4 <= rows; tt += 4) {
+                if (tt + 4 <= rows) {
+                    // groups of four frames, software pipelined: the operands of the NEXT group are loaded before the current
+                    // group's chain is issued, so no shared-memory latency is exposed between groups
                     float ph4[4], x4[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) { ph4[q] = php[q]; x4[q] = xp[q * xstep]; }
+                    for (; tt + 8 <= rows; tt += 4) {
+                        float pn[4], xn[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { pn[q] = php[4 + q]; xn[q] = xp[(4 + q) * xstep]; }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) frame(ph4[q], x4[q], q);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { ph4[q] = pn[q]; x4[q] = xn[q]; }
+                        php += 4; xp += 4 * xstep; sp_ptr += 4 * sB2;
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) frame(ph4[q], x4[q], q);
                     php += 4; xp += 4 * xstep; sp_ptr += 4 * sB2;
+                    tt += 4;
                 }
                 for (; tt < rows; ++tt) {
                     frame(php[0], xp[0], 0);
@@ -367,13 +380,24 @@ prefix_lazy_kernel(const LazyParams p, const __grid_constant__ CUtensorMap tmap)
                     int tt = (j == j0p) ? start_h - t0 : 0;
                     const float *php = pairs + ((size_t)(j & 1) * B + ph) * kPairP + (p_spec ? 1 : 0) + 2 * tt;
                     xp += tt * xstep;
-                    for (; tt + 4 <= rows; tt += 4) {
-                        float a4[4];
+                    if (tt + 4 <= rows) {
+                        float a4[4];                                   // software pipelined like the state loop
 #pragma unroll
                         for (int q = 0; q < 4; ++q) a4[q] = __fadd_rn(php[2 * q], xp[q * xstep]);
+                        for (; tt + 8 <= rows; tt += 4) {
+                            float an[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) an[q] = __fadd_rn(php[8 + 2 * q], xp[(4 + q) * xstep]);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) psi = logaddexp<kMath>(psi, a4[q], lut);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) a4[q] = an[q];
+                            php += 8; xp += 4 * xstep;
+                        }
 #pragma unroll
                         for (int q = 0; q < 4; ++q) psi = logaddexp<kMath>(psi, a4[q], lut);
                         php += 8; xp += 4 * xstep;
+                        tt += 4;
                     }
                     for (; tt < rows; ++tt) {
                         psi = logaddexp<kMath>(psi, __fadd_rn(php[0], xp[0]), lut);
@@ -462,14 +486,21 @@ extern "C" int e2e_ctc_prefix_step(const float *x, int Tmax, int U, int Vp, int 
         const char *e = getenv("E2E_LAZY_SMALL_TILE_FROM");          // tuning knob: utterances from which the 16-frame tile is used
         return e ? atoi(e) : 1500;       // measured: 16-frame tiles win from ~1500 utterances up, 32-frame tiles below (profiles/r02_e_prefix_micro_tiles.jsonl)
     }();
-    const bool small_tile = n_run >= small_from;
-    const int tile = small_tile ? 16 : 32;
+    static const int big_below = []() {
+        const char *e = getenv("E2E_LAZY_BIG_TILE_BELOW");           // tuning knob: utterances below which the 64-frame tile is used
+        return e ? atoi(e) : 200;
+    }();
+    // the deep tail (a handful of CTAs, each alone on its SM): 64-frame tiles halve the per-tile cost (barrier, mbarrier wait, set-up)
+    int tile = n_run >= small_from ? 16 : (n_run < big_below && !gather ? 64 : 32);
+    if (tile == 64 && lazy_smem_layout(gather, math, threads, Vp, B, 64).total > 96 * 1024) tile = 32;      // wide rows: keep the ring small
     LazyKernel kern;
-    if (fixed) kern = small_tile ? pick_math<false, true, 16, false>(math) : pick_math<false, true, 32, false>(math);
-    else if (gather) kern = small_tile ? (big ? pick_math<true, false, 16, true>(math) : pick_math<true, false, 16, false>(math))
+    if (fixed) kern = tile == 16 ? pick_math<false, true, 16, false>(math) : tile == 32 ? pick_math<false, true, 32, false>(math)
+                                                                                       : pick_math<false, true, 64, false>(math);
+    else if (gather) kern = tile == 16 ? (big ? pick_math<true, false, 16, true>(math) : pick_math<true, false, 16, false>(math))
                                        : (big ? pick_math<true, false, 32, true>(math) : pick_math<true, false, 32, false>(math));
-    else kern = small_tile ? (big ? pick_math<false, false, 16, true>(math) : pick_math<false, false, 16, false>(math))
-                           : (big ? pick_math<false, false, 32, true>(math) : pick_math<false, false, 32, false>(math));
+    else kern = tile == 16 ? (big ? pick_math<false, false, 16, true>(math) : pick_math<false, false, 16, false>(math))
+              : tile == 32 ? (big ? pick_math<false, false, 32, true>(math) : pick_math<false, false, 32, false>(math))
+                           : (big ? pick_math<false, false, 64, true>(math) : pick_math<false, false, 64, false>(math));
     const LazySmem L = lazy_smem_layout(gather, math, threads, Vp, B, tile);
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
