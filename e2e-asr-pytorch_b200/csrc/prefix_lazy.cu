@@ -486,21 +486,14 @@ extern "C" int e2e_ctc_prefix_step(const float *x, int Tmax, int U, int Vp, int 
         const char *e = getenv("E2E_LAZY_SMALL_TILE_FROM");          // tuning knob: utterances from which the 16-frame tile is used
         return e ? atoi(e) : 1500;       // measured: 16-frame tiles win from ~1500 utterances up, 32-frame tiles below (profiles/r02_e_prefix_micro_tiles.jsonl)
     }();
-    static const int big_below = []() {
-        const char *e = getenv("E2E_LAZY_BIG_TILE_BELOW");           // tuning knob: utterances below which the 64-frame tile is used
-        return e ? atoi(e) : 200;
-    }();
-    // the deep tail (a handful of CTAs, each alone on its SM): 64-frame tiles halve the per-tile cost (barrier, mbarrier wait, set-up)
-    int tile = n_run >= small_from ? 16 : (n_run < big_below && !gather ? 64 : 32);
-    if (tile == 64 && lazy_smem_layout(gather, math, threads, Vp, B, 64).total > 96 * 1024) tile = 32;      // wide rows: keep the ring small
+    // (64-frame tiles were measured for the deep tail — profiles/r02_o_prefix_micro_tiles64.jsonl: 1-4 % slower than 32; not built)
+    const int tile = n_run >= small_from ? 16 : 32;
     LazyKernel kern;
-    if (fixed) kern = tile == 16 ? pick_math<false, true, 16, false>(math) : tile == 32 ? pick_math<false, true, 32, false>(math)
-                                                                                       : pick_math<false, true, 64, false>(math);
+    if (fixed) kern = tile == 16 ? pick_math<false, true, 16, false>(math) : pick_math<false, true, 32, false>(math);
     else if (gather) kern = tile == 16 ? (big ? pick_math<true, false, 16, true>(math) : pick_math<true, false, 16, false>(math))
                                        : (big ? pick_math<true, false, 32, true>(math) : pick_math<true, false, 32, false>(math));
     else kern = tile == 16 ? (big ? pick_math<false, false, 16, true>(math) : pick_math<false, false, 16, false>(math))
-              : tile == 32 ? (big ? pick_math<false, false, 32, true>(math) : pick_math<false, false, 32, false>(math))
-                           : (big ? pick_math<false, false, 64, true>(math) : pick_math<false, false, 64, false>(math));
+                           : (big ? pick_math<false, false, 32, true>(math) : pick_math<false, false, 32, false>(math));
     const LazySmem L = lazy_smem_layout(gather, math, threads, Vp, B, tile);
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
