@@ -43,38 +43,6 @@ __device__ __forceinline__ float af_tanh(float x)
     return fmaf(-2.0f, r, 1.0f);
 }
 
-// Variant (E2E_AF_PAIR_RCP, measured in tools/sweep_prefix_variants.py attention): the channel loop of kernel A is bound by the
-// XU pipe (4 MUFU per hypothesis-frame-channel at 8 cycles per warp instruction per sub-partition = 32 cycles against 23 issue
-// slots).  Two hypotheses share ONE reciprocal: 1/a0 = a1 * (1/(a0*a1)), 1/a1 = a0 * (1/(a0*a1)), with exp(2x) clamped at 2^60
-// (tanh is 1.0f from 2^25 on) so that the product stays finite; and the factor 2/ln2 of exp(2x) = 2^(x*2/ln2) is folded into the
-// staged weights, queries and the inner tanh's output instead of one FMUL per evaluation.  3 MUFU and ~25 issue slots.
-#ifndef E2E_AF_PAIR_RCP
-#define E2E_AF_PAIR_RCP 0
-#endif
-constexpr float kAfExpScale = 2.8853900817779268f;             // 2 / ln 2
-
-// y[b] = out_scale * tanh(x[b] / kAfExpScale) for NB arguments that already carry the factor 2/ln2
-template <int NB>
-__device__ __forceinline__ void af_tanh_prescaled(const float (&x)[NB], float (&y)[NB], const float out_scale)
-{
-    if (NB == 1) {
-        float r;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex2_approx(x[0])));
-        y[0] = fmaf(-2.0f * out_scale, r, out_scale);
-    } else {
-#pragma unroll
-        for (int b = 0; b < NB; b += 2) {
-            const float a0 = 1.0f + fminf(ex2_approx(x[b]), 0x1p60f);
-            const float a1 = 1.0f + fminf(ex2_approx(x[(b + 1) % NB]), 0x1p60f);
-            float r;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a0 * a1));
-            r *= -2.0f * out_scale;
-            y[b] = fmaf(a1, r, out_scale);
-            y[(b + 1) % NB] = fmaf(a0, r, out_scale);
-        }
-    }
-}
-
 struct AttFullParams {
     const float *key_t, *value, *query, *prev_att; const int *enc_len;
     const float *w_conv, *w_proj, *w_energy; float b_energy, temperature;
@@ -124,14 +92,14 @@ attention_energy_kernel(const AttFullParams p)
         for (int k = 0; k < 16; ++k) w[k] = 0.0f;
 #pragma unroll
         for (int k = 0; k < kAfMaxK; ++k)
-            if (k < K) w[k] = __ldg(p.w_proj + (size_t)a * K + k) * (E2E_AF_PAIR_RCP ? kAfExpScale : 1.0f);
+            if (k < K) w[k] = __ldg(p.w_proj + (size_t)a * K + k);
         w[12] = __ldg(p.w_energy + a);
 #pragma unroll
         for (int q = 0; q < 4; ++q) cst[a * 4 + q] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
     }
     for (int i = tid; i < A * Bq; i += kAfThreads) {
         const int a = i / Bq, b = i - a * Bq;
-        qs[i] = (b < B) ? __ldg(p.query + ((size_t)u * B + b) * A + a) * (E2E_AF_PAIR_RCP ? kAfExpScale : 1.0f) : 0.0f;
+        qs[i] = (b < B) ? __ldg(p.query + ((size_t)u * B + b) * A + a) : 0.0f;
     }
     __syncthreads();
 
@@ -194,22 +162,6 @@ attention_energy_kernel(const AttFullParams p)
                     } else {
                         qq[0] = qs[a * Bq + b0];
                     }
-#if E2E_AF_PAIR_RCP
-                    float loc[NB], th[NB];
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) {
-                        loc[b] = wp[0] * f[b][0];
-#pragma unroll
-                        for (int k = 1; k < KP; ++k) loc[b] = fmaf(wp[k], f[b][k], loc[b]);
-                    }
-                    af_tanh_prescaled<NB>(loc, th, kAfExpScale);
-                    const float ks = kk[i] * kAfExpScale;
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) loc[b] = (ks + qq[b]) + th[b];
-                    af_tanh_prescaled<NB>(loc, th, 1.0f);
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) acc[b] = fmaf(we, th[b], acc[b]);
-#else
 #pragma unroll
                     for (int b = 0; b < NB; ++b) {
                         float loc = wp[0] * f[b][0];
@@ -218,7 +170,6 @@ attention_energy_kernel(const AttFullParams p)
                         const float x = (kk[i] + qq[b]) + af_tanh(loc);
                         acc[b] = fmaf(we, af_tanh(x), acc[b]);
                     }
-#endif
                 }
             }
 #pragma unroll

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(1024) k_thr(float *out, long long *cyc, float 
         for (int q = 0; q < 8; ++q) {
             float y;
             if (KIND == 0) asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v[q]));
-            else if (KIND == 1) asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v[q]));
+            else if (KIND == 1) { asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v[q])); y += 0.75f; }     // (+ FADD: rcp(rcp(x)) alone is folded away)
             else y = fmaf(v[q], e, 0.25f);
             v[q] = y;
         }
