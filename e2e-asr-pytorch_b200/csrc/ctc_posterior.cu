@@ -194,19 +194,31 @@ ctc_log_softmax_wide_kernel(const float *__restrict__ logits, int U, int Tmax, i
     }
 }
 
-// One thread per utterance: the reference's running sum is sequential fp32 (src/ctc.py:24-26),
-// so the adds are kept in that order.  r0: [U][Tmax][1][2].
-__global__ void ctc_init_state_kernel(const float *__restrict__ x, int Tmax, int U, int Vp,
-                                      const int *__restrict__ enc_len, float2 *__restrict__ r0)
+// One warp per utterance.  The reference's running sum is sequential fp32 (src/ctc.py:24-26), so the adds are kept in
+// that order: the lanes load 32 frames' blank scores at once (independent loads), every lane then replays the 32 adds
+// from shuffles (the chain is one FADD per frame) and keeps the partial sum of its own frame, and the 32 states leave
+// as one 256-byte store.  r0: [U][Tmax][1][2].
+constexpr int kInitWarps = 4;
+__global__ void __launch_bounds__(kInitWarps * 32)
+ctc_init_state_kernel(const float *__restrict__ x, int Tmax, int U, int Vp, const int *__restrict__ enc_len, float2 *__restrict__ r0)
 {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int u = blockIdx.x * kInitWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (u >= U) return;
-    const int tu = enc_len ? enc_len[u] : Tmax;
+    const int tu = enc_len ? min(enc_len[u], Tmax) : Tmax;
+    const float *xb = x + (long long)u * Vp + E2E_CTC_BLANK;
     float acc = 0.0f;
-    for (int t = 0; t < tu; ++t) {
-        const float b = __ldg(x + ((long long)t * U + u) * Vp + E2E_CTC_BLANK);
-        acc = (t == 0) ? b : __fadd_rn(acc, b);
-        r0[(long long)u * Tmax + t] = make_float2(E2E_CTC_LOGZERO, acc);
+    float nxt = (lane < tu) ? __ldg(xb + (long long)lane * U * Vp) : 0.0f;
+    for (int t0 = 0; t0 < tu; t0 += 32) {
+        const float cur = nxt;
+        if (t0 + 32 + lane < tu) nxt = __ldg(xb + (long long)(t0 + 32 + lane) * U * Vp);      // next group in flight under the chain
+        float mine = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float b = __shfl_sync(0xffffffffu, cur, i);
+            acc = (t0 + i == 0) ? b : __fadd_rn(acc, b);
+            if (i == lane) mine = acc;
+        }
+        if (t0 + lane < tu) r0[(long long)u * Tmax + t0 + lane] = make_float2(E2E_CTC_LOGZERO, mine);
     }
 }
 
@@ -253,7 +265,7 @@ extern "C" int e2e_ctc_init_state(const float *x, int Tmax, int U, int Vp, const
     using namespace e2e;
     if (!x || !r0 || U <= 0 || Tmax <= 0 || Vp <= 0) return set_error(E2E_ERR_ARG, "e2e_ctc_init_state: bad argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    ctc_init_state_kernel<<<(U + 127) / 128, 128, 0, st>>>(x, Tmax, U, Vp, enc_len, reinterpret_cast<float2 *>(r0));
+    ctc_init_state_kernel<<<(U + kInitWarps - 1) / kInitWarps, kInitWarps * 32, 0, st>>>(x, Tmax, U, Vp, enc_len, reinterpret_cast<float2 *>(r0));
     count_launch();
     return check_launch("e2e_ctc_init_state");
 }
