@@ -476,6 +476,34 @@ def cpu_arm():
         return PortCpu()
 
 
+def cpu_prefix_only(kind, frames=640, budget_s=3.0):
+    """Kernel-level figure of the CPU arm (SURVEY §8d "cheap_compute-only timing"): the reference's numpy
+    ``CTCPrefixScore.cheap_compute`` (src/ctc.py:68-108) alone, one core, a chain of calls on a median-length utterance
+    with the bench's C = 12 candidates — the unit (candidate-frames per second) of ``roofline.cand_frames_per_s``."""
+    if kind == "port":
+        from oracle.ctc_prefix_oracle import PrefixScorerOracle as CTCPrefixScore
+    else:
+        from oracle import refload
+        CTCPrefixScore = refload.load().CTCPrefixScore
+    T, C = frames // 4, int(1.5 * BEAM)
+    g = torch.Generator().manual_seed(7)
+    x = torch.log_softmax(torch.randn(1, T, VOCAB, generator=g), -1)
+    sc = CTCPrefixScore(x)
+    rng = np.random.default_rng(7)
+    calls, t0 = 0, time.time()
+    while time.time() - t0 < budget_s:                                            # one decode after the other until the budget is spent
+        r, prefix = sc.init_state(), []
+        while time.time() - t0 < budget_s and len(prefix) < T // 5:               # max_len_ratio 0.2 of L = 4 T
+            cands = [int(c) for c in rng.permutation(VOCAB - 1)[:C] + 1]
+            for _ in range(BEAM):                                                 # the beam's hypotheses share the step
+                psi, r_new = sc.cheap_compute(prefix, r, cands)
+                calls += 1
+            prefix, r = prefix + [cands[0]], r_new[0]
+    wall = time.time() - t0
+    return {"cand_frames_per_s": calls * C * T / wall, "cores": 1,
+            "sample": "%d cheap_compute calls (T = %d frames, C = %d, prefixes of 0..%d tokens) in %.1f s" % (calls, T, C, T // 5 - 1, wall)}
+
+
 def cpu_baseline(args, sample_utts=None):
     """Bounded CPU figure printed beside the B200 line: one median-length utterance per core."""
     cores = len(os.sched_getaffinity(0))
@@ -493,7 +521,8 @@ def cpu_baseline(args, sample_utts=None):
                       "`bench.py --impl reference` decodes a length-stratified sample of the set itself"
                       % (n_jobs, frames, frames / 100.0, MEDIAN_NOTE if frames == 640 else "",
                          {"staged": "oracle/_ref", "live": "/root/reference", "port": "NOT AVAILABLE HERE: oracle port, oracle/beam_oracle.py"}[ref.kind], procs, wall),
-            "cand_frames_per_s": sum(cand_frames(n) for _, n in jobs) / wall}
+            "cand_frames_per_s": sum(cand_frames(n) for _, n in jobs) / wall,
+            "prefix_only": cpu_prefix_only(ref.kind)}
 
 
 def run_reference(args):
@@ -548,7 +577,8 @@ def run_reference(args):
         "config": {"workload": "cfg2: char V=31 VGG+BLSTM CTC-attention (librispeech_asr.yaml dims, vgg=1) + 4x1024 RNNLM, "
                                "beam 8, ctc 0.5, lm 0.5, max_len_ratio 0.2, dev-clean-like lengths, random init; bounded sample: " + sample},
         "cpu_baseline": {"value": value, "unit": "utts/s", "cores": procs, "kind": "reference" if ref.kind != "port" else "port", "cpu": cpu_model_name(),
-                         "sample": sample, "cand_frames_per_s": units / wall, "wall_s": wall, "as_shipped": shipped},
+                         "sample": sample, "cand_frames_per_s": units / wall, "wall_s": wall, "as_shipped": shipped,
+                         "prefix_only": cpu_prefix_only(ref.kind)},
         "e2e": {"value": value, "unit": "utts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 

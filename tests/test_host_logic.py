@@ -232,6 +232,8 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 2 and d["gpu_launches"] == 0
     assert "unmodified reference" in d["cpu_baseline"]["sample"] and "quantile" not in d["cpu_baseline"]["sample"]   # fixed-length smoke sample
     assert d["cpu_baseline"]["as_shipped"]["n_jobs"] == 4 and d["cpu_baseline"]["as_shipped"]["value"] > 0
+    po = d["cpu_baseline"]["prefix_only"]                          # cheap_compute alone, the kernel-level CPU figure
+    assert po["cores"] == 1 and 1e4 < po["cand_frames_per_s"] < 1e9 and "cheap_compute" in po["sample"]
     quiet = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert quiet.returncode == 0 and quiet.stdout.strip() == ""
 
