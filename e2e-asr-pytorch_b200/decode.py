@@ -18,7 +18,8 @@ the reference fans single utterances out to joblib processes
 (``bin/test_asr.py:138-139``); here they share every kernel launch.
 
 Per decode step the device runs: the batched PyTorch model step (``stepper.py``),
-then (3a) ``e2e_beam_candidates``, (2) ``e2e_ctc_prefix_score``, (3b)
+then (3a) ``e2e_beam_candidates``, (2) ``e2e_ctc_prefix_step`` (the fused lazy prefix
+kernel; ``e2e_ctc_prefix_score``, the eager one, with ``lazy_prefix = False``), (3b)
 ``e2e_beam_combine_prune``; the posteriors come from (1) ``e2e_ctc_log_softmax``
 once per batch.  Nothing is copied to the host until the final N-best.
 There is no CPU fallback: inputs must live on a CUDA device.
@@ -182,6 +183,9 @@ class BeamDecoder(nn.Module):
         on the first chunk while the rest is still in flight (one event per chunk).  ``last_h2d_bytes`` holds the bytes copied."""
         if audio_feature.is_cuda:
             return self.decode_batch(audio_feature, feature_len, return_arrays)
+        if audio_feature.shape[0] == 0 and len(feature_len) == 0:      # an empty shard
+            self.last_h2d_bytes = 0
+            return self._no_utterances(torch.device(device) if return_arrays == "device" else "cpu", return_arrays)
         if not audio_feature.is_pinned():
             raise ValueError("decode_batch_from_host needs pinned host features (torch.Tensor.pin_memory): pageable memory "
                              "would turn every copy into a synchronous one")
@@ -247,9 +251,20 @@ class BeamDecoder(nn.Module):
         (no read-back: the sharded driver packs and gathers them on the device)."""
         if not audio_feature.is_cuda:
             raise L.E2EError("BeamDecoder has no CPU path: move the features and the decoder to a CUDA device")
+        if audio_feature.shape[0] == 0:                                # an empty shard: nothing to launch
+            return self._no_utterances(audio_feature.device if return_arrays == "device" else "cpu", return_arrays)
         # the hand-written kernels are enqueued on the CURRENT device's current stream: make the features' device current
         with torch.cuda.device(audio_feature.device):
             return self._decode_batch(audio_feature, feature_len, return_arrays)
+
+    def _no_utterances(self, where, return_arrays):
+        self.last_stats = {"utterances": 0, "steps": 0, "enc_frames": [], "cand_frames": 0}
+        if not return_arrays:
+            return []
+        b = self.beam_size
+        return (torch.zeros((0, b, 1), dtype=torch.int32, device=where), torch.zeros((0, b, 1), dtype=torch.float32, device=where),
+                torch.zeros((0, b), dtype=torch.int32, device=where), torch.zeros((0, b), dtype=torch.float32, device=where),
+                torch.zeros((0,), dtype=torch.int32, device=where))
 
     def _decode_batch(self, audio_feature, feature_len, return_arrays):
         dev = audio_feature.device

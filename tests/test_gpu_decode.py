@@ -201,6 +201,22 @@ def test_decode_batch_is_order_independent(cuda):
         assert [h.outIndex for h in alone] == [h.outIndex for h in both[k]], k
 
 
+def test_decode_batch_of_no_utterances(cuda):
+    """An empty shard (more ranks than utterances) decodes to nothing, in every return form, without a launch."""
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth, _lib
+    asr = synth.build_asr(31, synth.TINY_ASR_CFG, seed=0, peak=4.0)
+    dec = BeamDecoder(asr, None, 4, 0.01, 0.2, ctc_weight=0.5).to(cuda)
+    feat, fl = torch.zeros(0, 0, synth.FEAT_DIM), torch.zeros(0, dtype=torch.long)
+    before = _lib.load().e2e_launch_count()
+    assert dec.decode_batch(feat.to(cuda), fl.to(cuda)) == []
+    for form in (True, "device"):
+        tok, sc, ln, avg, n = dec.decode_batch(feat.to(cuda), fl.to(cuda), return_arrays=form)
+        assert tok.shape[:2] == (0, 4) and sc.shape[:2] == (0, 4) and ln.shape == (0, 4) and avg.shape == (0, 4) and n.shape == (0,)
+        assert tok.is_cuda == (form == "device")
+    assert dec.decode_batch_from_host(feat, fl, cuda) == []
+    assert _lib.load().e2e_launch_count() == before and dec.last_stats["utterances"] == 0
+
+
 def test_decode_dataset_feeds_the_reference_result_files(cuda, tmp_path):
     """f-3: decode_dataset + write_results reproduce the reference's per-utterance flow (bin/test_asr.py:138-156):
     same tuples as one-utterance-per-call decoding, files in the reference's layout, scorable by results.score_file."""

@@ -272,3 +272,14 @@ def test_ragged_nbest_buffer_layout_and_size():
     one = shard.plan_shards(big, 1, 0.2)
     cap = int(np.ceil(big.max() * 0.2)) + 1
     assert shard.ragged_size(one, big, 8, 0.2) * 4.0 < 2620 * shard.row_width(8, cap) * 4 / 4.0
+
+
+def test_empty_shard_decodes_to_nothing_without_a_device():
+    """decode_batch_from_host on an empty shard returns before any device work (a rank with no utterances)."""
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth
+    dec = BeamDecoder(synth.build_asr(31, synth.TINY_ASR_CFG, seed=0), None, 4, 0.01, 0.2, ctc_weight=0.5)
+    feat, fl = torch.zeros(0, 0, synth.FEAT_DIM), torch.zeros(0, dtype=torch.long)
+    assert dec.decode_batch_from_host(feat, fl, "cuda:0") == []
+    tok, sc, ln, avg, n = dec.decode_batch_from_host(feat, fl, "cuda:0", return_arrays=True)
+    assert tok.shape == (0, 4, 1) and sc.shape == (0, 4, 1) and ln.shape == (0, 4) and avg.shape == (0, 4) and n.shape == (0,)
+    assert dec.last_stats["utterances"] == 0 and dec.last_h2d_bytes == 0
