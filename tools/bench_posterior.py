@@ -55,6 +55,19 @@ def main():
     except Exception:
         pass
     gbs = bytes_alg / (ms.mean() * 1e-3) / 1e9
+    # the empty-prefix state from the posteriors just written (e2e_ctc_init_state): 4 bytes read (one 32-byte sector in HBM terms)
+    # and 8 written per valid frame
+    r0 = ops.ctc_init_state(x, enc_len)
+    torch.cuda.synchronize()
+    ms0 = []
+    for _ in range(a.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops.ctc_init_state(x, enc_len, out=r0); e1.record()
+        torch.cuda.synchronize()
+        ms0.append(e0.elapsed_time(e1))
+    print(json.dumps({"kernel": "ctc_init_state", "utts": U, "frames": T, "vocab": V, "ragged": a.ragged, "ms_mean": float(np.mean(ms0)),
+                      "ms_min": float(np.min(ms0)), "frame_rows": rows, "GBps_12_bytes_per_frame": rows * 12.0 / (float(np.mean(ms0)) * 1e-3) / 1e9}))
     print(json.dumps({"kernel": "ctc_log_softmax", "utts": U, "frames": T, "vocab": V, "ragged": a.ragged, "ms_mean": float(ms.mean()),
                       "ms_min": float(ms.min()), "frame_rows": rows, "bytes_per_frame_row": 8.0 * V + 4.0, "algorithmic_GBps": gbs,
                       "frac_of_measured_hbm_peak": gbs / peak, "l2": "flushed between timed launches (256 MB write)"}))
