@@ -60,7 +60,7 @@ extern "C" {
 #define E2E_PREFIX_ROW_COPIES    16 /* stage posterior tiles with one bulk copy per row instead of one
                                        tensor-map box copy per tile (cross-check of the TMA path)       */
 #define E2E_PREFIX_POLY_MATH     32 /* MUFU ex2 + degree-8 polynomial log-add-exp (no table; polynomial error
-                                       3.3e-8; opt-in experiment, see csrc/common.cuh)                   */
+                                       3.3e-8; what BeamDecoder passes by default, see csrc/common.cuh)  */
 #define E2E_PREFIX_POLY_ESTRIN   64 /* with E2E_PREFIX_POLY_MATH: evaluate the polynomial pairwise (shorter
                                        dependent chain, 2 more instructions)                             */
 
