@@ -52,3 +52,41 @@ def test_fullsize_models_match_the_reference_nbest(cuda, tmp_path):
         same, ties = same + s, ties + t
     print("full-size models: identical 1-best %d/%d, score ties %d (every other outcome fails the test)" % (same, len(order), ties))
     assert same + ties == len(order) and same >= (2 * len(order)) // 3
+
+
+def test_cfg1_fullsize_matches_the_reference_nbest(cuda):
+    """BASELINE configs[0], the reference's own CPU-runnable case (beam 2 -> 3 CTC candidates, CTC weight 0.5, no LM, 10-second
+    utterances, the full-size model): six utterances the UNMODIFIED reference decoded in the build container
+    (tests/golden/beam_nbest_cfg1.npz, tools/make_golden.py cfg1).  Runner-up gaps are 1e-5 .. 1e-4 in mean score, so a
+    different 1-best is accepted only as a tie by the oracle's own rescoring of the device's sequence."""
+    import copy
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth
+    from oracle import beam_oracle as BO
+    from tests.test_gpu_decode import _compare
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "beam_nbest_cfg1.npz"), allow_pickle=False)
+    beam, ctc_w = int(gold["beam"]), float(gold["ctc_w"])
+    asr = synth.build_asr(31, seed=0)
+    asr_cpu = copy.deepcopy(asr)
+    dec = BeamDecoder(asr, None, beam, 0.01, 0.2, ctc_weight=ctc_w).to(cuda)
+    assert dec.ctc_beam_size == 3 and not dec.apply_lm
+    cases = list(range(int(gold["n_cases"])))
+    utts = [int(gold["case%d_utt" % c]) for c in cases]
+    lens = [int(gold["case%d_len" % c]) for c in cases]
+    feat, fl = synth.padded_batch(utts, lens)
+    out = dec.decode_batch(feat.to(cuda), fl.to(cuda))
+    same = ties = 0
+    for c in cases:
+        ref = [(gold["case%d_tok%d" % (c, j)], gold["case%d_sc%d" % (c, j)], gold["case%d_avg%d" % (c, j)])
+               for j in range(int(gold["case%d_nbest" % c]))]
+        assert len(out[c]) == len(ref)
+
+        def rescore(ids, c=c):
+            with torch.no_grad():
+                h = BO.decode_utterance(asr_cpu, synth.utterance(utts[c], lens[c])[None], torch.LongTensor([lens[c]]), beam, 0.01, 0.2,
+                                        ctc_weight=ctc_w, force=ids)[0]
+            return h.mean_score()
+
+        s, t = _compare(out[c], ref, "cfg1 case %d (utt %d)" % (c, utts[c]), rescore=rescore)
+        same, ties = same + s, ties + t
+    print("cfg1 full-size: identical 1-best %d/%d, score ties %d (every other outcome fails the test)" % (same, len(cases), ties))
+    assert same + ties == len(cases)

@@ -122,12 +122,39 @@ def fullsize_cases(n_set=16):
 _FS = {}
 
 
-def _fullsize_worker(job):
+CFG1_CASES = [(910001 + i, 1000) for i in range(6)]        # BASELINE configs[0]: 10-second utterances, beam 2, no LM
+
+
+def _cfg1_worker(job):
+    return _fullsize_worker(job, beam=2, lm_w=0.0, slot="dec_cfg1")
+
+
+def beam_nbest_cfg1(procs=6):
+    """BASELINE configs[0] (the reference's own CPU-runnable case): V = 31, beam 2 (3 CTC candidates), CTC weight 0.5, no
+    LM, 1000 input frames, the full-size model — six utterances through the unmodified reference."""
+    import multiprocessing as mp
+    jobs = [(k, utt, n) for k, (utt, n) in enumerate(CFG1_CASES)]
+    with mp.get_context("fork").Pool(procs) as pool:
+        res = dict(pool.imap_unordered(_cfg1_worker, jobs))
+    out = {"beam": np.int32(2), "lm_w": np.float32(0.0), "ctc_w": np.float32(0.5), "n_cases": np.int32(len(jobs))}
+    for k, (utt, n) in enumerate(CFG1_CASES):
+        hyps = res[k]
+        key = "case%d" % k
+        out[key + "_utt"], out[key + "_len"], out[key + "_nbest"] = np.int32(utt), np.int32(n), np.int32(len(hyps))
+        for j, (tok, sc, avg) in enumerate(hyps):
+            out["%s_tok%d" % (key, j)], out["%s_sc%d" % (key, j)], out["%s_avg%d" % (key, j)] = tok, sc, avg
+        print("  cfg1 case %d: utt %d, %d frames, %d tokens, best mean score %.6f, runner-up gap %.3g"
+              % (k, utt, n, len(hyps[0][0]), float(hyps[0][2]), float(hyps[0][2]) - float(hyps[1][2])), flush=True)
+    np.savez_compressed(os.path.join(OUT, "beam_nbest_cfg1.npz"), **out)
+    print("beam_nbest_cfg1.npz: %d cases" % len(jobs))
+
+
+def _fullsize_worker(job, beam=8, lm_w=0.5, slot="dec"):
     k, utt, n = job
     torch.set_num_threads(1)
-    if "dec" not in _FS:
+    if slot not in _FS:
         ref = refload.load()
-        vocab, beam, lm_w, ctc_w = 31, 8, 0.5, 0.5
+        vocab, ctc_w = 31, 0.5
         mine = synth.build_asr(vocab, seed=0)
         rasr = ref.ASR(synth.FEAT_DIM, vocab, True, **copy.deepcopy(synth.ASR_MODEL_CFG)).eval()
         rasr.load_state_dict(mine.state_dict())
@@ -135,10 +162,10 @@ def _fullsize_worker(job):
         tmp = tempfile.mkdtemp()
         torch.save({"model": lm.state_dict()}, os.path.join(tmp, "lm.pth"))
         yaml.safe_dump({"model": synth.LM_MODEL_CFG}, open(os.path.join(tmp, "lm.yaml"), "w"))
-        _FS["dec"] = ref.BeamDecoder(rasr, None, beam, 0.01, 0.2, lm_path=os.path.join(tmp, "lm.pth"),
-                                     lm_config=os.path.join(tmp, "lm.yaml"), lm_weight=lm_w, ctc_weight=ctc_w)
+        _FS[slot] = ref.BeamDecoder(rasr, None, beam, 0.01, 0.2, lm_path=os.path.join(tmp, "lm.pth"),
+                                    lm_config=os.path.join(tmp, "lm.yaml"), lm_weight=lm_w, ctc_weight=ctc_w)
     with torch.no_grad():
-        hyps = _FS["dec"](synth.utterance(utt, n)[None], torch.LongTensor([n]))
+        hyps = _FS[slot](synth.utterance(utt, n)[None], torch.LongTensor([n]))
     return k, [(np.array(h.outIndex, np.int32), np.array([float(s) for s in h.output_scores], np.float32),
                 np.float32(float(h.avgScore()))) for h in hyps]
 
@@ -169,7 +196,10 @@ if __name__ == "__main__":
     torch.set_num_threads(4)
     if len(sys.argv) > 1 and sys.argv[1] == "fullsize":      # leaves the other fixtures untouched
         beam_nbest_fullsize(ref)
+    elif len(sys.argv) > 1 and sys.argv[1] == "cfg1":
+        beam_nbest_cfg1()
     else:
         prefix_chains(ref)
         beam_nbest(ref)
         beam_nbest_fullsize(ref)
+        beam_nbest_cfg1()
