@@ -259,6 +259,28 @@ def test_decode_large_vocab_and_wide_beam_match_oracle(cuda, vocab, beam, lm_w, 
     assert same >= len(lens) - 1
 
 
+@pytest.mark.parametrize("vocab,beam,lm_w,lens,lazy", [(31, 4, 0.3, [64, 120, 92, 148], False),      # the eager kernel by choice
+                                                        (300, 24, 0.0, [64, 100, 80], True)])         # ... and by routing: beam 24 does not fit one CTA
+def test_decode_through_the_eager_prefix_kernel_matches_oracle(cuda, vocab, beam, lm_w, lens, lazy):
+    """The decode loop's other prefix path: e2e_ctc_prefix_score (a state for every candidate, round 1's kernel) — what
+    ``lazy_prefix = False`` selects and what beams whose lanes do not fit the fused kernel's CTA (B > 20) fall back to."""
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth, ops
+    asr, lm, lm_path, lm_cfg = _models(vocab=vocab)
+    feat, fl = synth.padded_batch(list(range(len(lens))), lens)
+    dec = BeamDecoder(asr, None, beam, 0.01, 0.2, lm_path=lm_path, lm_config=lm_cfg, lm_weight=lm_w, ctc_weight=0.5).to(cuda)
+    dec.lazy_prefix = lazy
+    assert lazy == (not ops.prefix_step_supported(vocab, beam, dec.ctc_beam_size))      # either switched off or not supported
+    out = dec.decode_batch(feat.to(cuda), fl.to(cuda))
+    same = ties = 0
+    for k, n in enumerate(lens):
+        ora = _oracle_nbest(asr, lm, feat[k], n, beam, lm_w, 0.5)
+        assert len(out[k]) == len(ora)
+        s, t = _compare(out[k], ora, "eager path V %d beam %d utt %d" % (vocab, beam, k))
+        same, ties = same + s, ties + t
+    print("eager prefix path, V %d beam %d: identical 1-best %d/%d, ties %d" % (vocab, beam, same, len(lens), ties))
+    assert same >= len(lens) - 1
+
+
 class _COracleScorer:
     """The prefix scorer interface of oracle/ctc_prefix_oracle.py on top of the plain-C oracle (bit-identical, tests/
     test_oracle_golden.py; its frame loop is compiled, which the long-form case needs)."""
