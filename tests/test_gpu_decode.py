@@ -281,6 +281,31 @@ def test_decode_through_the_eager_prefix_kernel_matches_oracle(cuda, vocab, beam
     assert same >= len(lens) - 1
 
 
+@pytest.mark.parametrize("eos_bias,ctc_w,lm_w,ids", [(0.0, 0.0, 0.0, [0, 1, 2, 3]),      # greedy, closes as soon as <eos> wins (decode.py:169-170)
+                                                      (4.0, 0.0, 0.3, [0, 1, 2, 3]),      # <eos> wins before min_len: closed hypothesis dropped, no child -> empty N-best
+                                                      (0.0, 0.5, 0.3, [0, 1, 3])])        # one CTC candidate (utterance 2 is in the crash envelope, decode.py:252)
+def test_decode_beam_1(cuda, eos_bias, ctc_w, lm_w, ids):
+    """beam_size = 1 (one CTC candidate): the reference returns at the first closed hypothesis (decode.py:169-170); the device
+    path reaches the same N-best because a closed beam-1 hypothesis leaves no child behind."""
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth
+    asr, lm, lm_path, lm_cfg = _models()
+    with torch.no_grad():
+        asr.decoder.char_trans.bias[1] += eos_bias
+    all_lens = [64, 120, 92, 148]
+    lens = [all_lens[i] for i in ids]
+    feat, fl = synth.padded_batch(ids, lens)
+    dec = BeamDecoder(asr, None, 1, 0.01, 0.2, lm_path=lm_path, lm_config=lm_cfg, lm_weight=lm_w, ctc_weight=ctc_w).to(cuda)
+    out = dec.decode_batch(feat.to(cuda), fl.to(cuda))
+    for k, n in enumerate(lens):
+        ora = _oracle_nbest(asr, lm, feat[k], n, 1, lm_w, ctc_w)
+        assert [len(h.outIndex) for h in out[k]] == [len(o[0]) for o in ora], (k, [h.outIndex for h in out[k]], [o[0].tolist() for o in ora])
+        if ora:
+            s, t = _compare(out[k], ora, "beam 1 utt %d" % ids[k])
+            assert s == 1
+    if eos_bias > 0:
+        assert all(len(o) == 0 for o in out)        # the fixture is the empty-N-best case
+
+
 class _COracleScorer:
     """The prefix scorer interface of oracle/ctc_prefix_oracle.py on top of the plain-C oracle (bit-identical, tests/
     test_oracle_golden.py; its frame loop is compiled, which the long-form case needs)."""
