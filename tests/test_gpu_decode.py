@@ -306,6 +306,30 @@ def test_decode_beam_1(cuda, eos_bias, ctc_w, lm_w, ids):
         assert all(len(o) == 0 for o in out)        # the fixture is the empty-N-best case
 
 
+@pytest.mark.parametrize("mode,v_proj", [("dot", False), ("loc", True)])
+def test_decode_other_attention_configurations(cuda, mode, v_proj):
+    """The reference's other attention settings (config key attention.mode = 'dot': scaled-dot energies, plain PyTorch in
+    the batched stepper; attention.v_proj: projected values in the fused location-aware kernel) decode like the oracle."""
+    import copy
+    from e2e_asr_pytorch_b200 import BeamDecoder, synth
+    cfg = copy.deepcopy(synth.TINY_ASR_CFG)
+    cfg["attention"]["mode"], cfg["attention"]["v_proj"] = mode, v_proj
+    asr = synth.build_asr(31, cfg, seed=0, peak=4.0)
+    _, lm, lm_path, lm_cfg = _models()
+    lens = [64, 120, 92, 148]
+    feat, fl = synth.padded_batch(list(range(len(lens))), lens)
+    dec = BeamDecoder(asr, None, 4, 0.01, 0.2, lm_path=lm_path, lm_config=lm_cfg, lm_weight=0.3, ctc_weight=0.5).to(cuda)
+    out = dec.decode_batch(feat.to(cuda), fl.to(cuda))
+    same = ties = 0
+    for k, n in enumerate(lens):
+        ora = _oracle_nbest(asr, lm, feat[k], n, 4, 0.3, 0.5)
+        assert len(out[k]) == len(ora)
+        s, t = _compare(out[k], ora, "attention %s v_proj %s utt %d" % (mode, v_proj, k))
+        same, ties = same + s, ties + t
+    print("attention %s, v_proj %s: identical 1-best %d/%d, ties %d" % (mode, v_proj, same, len(lens), ties))
+    assert same >= len(lens) - 1
+
+
 class _COracleScorer:
     """The prefix scorer interface of oracle/ctc_prefix_oracle.py on top of the plain-C oracle (bit-identical, tests/
     test_oracle_golden.py; its frame loop is compiled, which the long-form case needs)."""

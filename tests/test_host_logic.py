@@ -36,10 +36,16 @@ def test_beam_decoder_constructor_surface(tmp_path):
     assert h.outIndex == [5, 6, 1] and float(h.avgScore()) == -2.0 and len(h.output_scores) == 3
 
 
-def test_batched_stepper_matches_per_hypothesis_modules():
+@pytest.mark.parametrize("mode,v_proj", [("loc", False), ("dot", False), ("loc", True)])
+def test_batched_stepper_matches_per_hypothesis_modules(mode, v_proj):
+    """The batched model step against the modules called one hypothesis at a time, as the reference does (decode.py:105-123,
+    144-151): location-aware and scaled-dot attention (config key attention.mode), with and without the value projection."""
+    import copy
     from e2e_asr_pytorch_b200 import synth
     from e2e_asr_pytorch_b200.stepper import BatchedStepper
-    asr = synth.build_asr(31, synth.TINY_ASR_CFG, seed=0, peak=4.0)
+    cfg = copy.deepcopy(synth.TINY_ASR_CFG)
+    cfg["attention"]["mode"], cfg["attention"]["v_proj"] = mode, v_proj
+    asr = synth.build_asr(31, cfg, seed=0, peak=4.0)
     lm = synth.build_lm(31, synth.TINY_LM_CFG, seed=1)
     lens, beam = [64, 120, 92], 3
     feat, fl = synth.padded_batch([3, 4, 5], lens)
@@ -60,7 +66,7 @@ def test_batched_stepper_matches_per_hypothesis_modules():
             lg, _ = asr.decoder(torch.cat([asr.pre_embed(torch.LongTensor([0])), ctx], -1))
             lmo, lmh = lm(torch.LongTensor([[0]]), torch.ones([1]), hidden=None)
             assert torch.allclose(lg[0], a1[u * beam], atol=2e-6) and torch.allclose(lmo[0, 0], l1[u * beam], atol=2e-6)
-            dstate, pa = asr.decoder.get_state(), asr.attention.att_layer.prev_att
+            dstate, pa = asr.decoder.get_state(), getattr(asr.attention.att_layer, "prev_att", None)
             for b, tk in enumerate(toks):
                 asr.set_state(dstate, pa)
                 _, ctx2 = asr.attention(asr.decoder.get_query(), e, el)
