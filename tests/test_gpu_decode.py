@@ -306,14 +306,21 @@ def test_decode_beam_1(cuda, eos_bias, ctc_w, lm_w, ids):
         assert all(len(o) == 0 for o in out)        # the fixture is the empty-N-best case
 
 
-@pytest.mark.parametrize("mode,v_proj", [("dot", False), ("loc", True)])
-def test_decode_other_attention_configurations(cuda, mode, v_proj):
-    """The reference's other attention settings (config key attention.mode = 'dot': scaled-dot energies, plain PyTorch in
-    the batched stepper; attention.v_proj: projected values in the fused location-aware kernel) decode like the oracle."""
+@pytest.mark.parametrize("mode,v_proj,variant", [("dot", False, ""), ("loc", True, ""), ("loc", False, "yaml_encoder"), ("loc", False, "gru")])
+def test_decode_other_model_configurations(cuda, mode, v_proj, variant):
+    """The reference's other model settings decode like the oracle: attention.mode = 'dot' (scaled-dot energies, plain PyTorch
+    in the batched stepper), attention.v_proj (projected values in the fused location-aware kernel), the encoder of
+    config/librispeech_asr.yaml as written (no VGG, a layer that drops every other frame: the unpacked encoder path), GRU
+    encoder layers and a 2-layer GRU speller (the plain PyTorch cells of the stepper)."""
     import copy
     from e2e_asr_pytorch_b200 import BeamDecoder, synth
     cfg = copy.deepcopy(synth.TINY_ASR_CFG)
     cfg["attention"]["mode"], cfg["attention"]["v_proj"] = mode, v_proj
+    if variant == "yaml_encoder":
+        cfg["encoder"].update({"vgg": 0, "sample_rate": [1, 2], "sample_style": "drop"})
+    elif variant == "gru":
+        cfg["encoder"]["module"] = "GRU"
+        cfg["decoder"].update({"module": "GRU", "layer": 2})
     asr = synth.build_asr(31, cfg, seed=0, peak=4.0)
     _, lm, lm_path, lm_cfg = _models()
     lens = [64, 120, 92, 148]
@@ -324,9 +331,9 @@ def test_decode_other_attention_configurations(cuda, mode, v_proj):
     for k, n in enumerate(lens):
         ora = _oracle_nbest(asr, lm, feat[k], n, 4, 0.3, 0.5)
         assert len(out[k]) == len(ora)
-        s, t = _compare(out[k], ora, "attention %s v_proj %s utt %d" % (mode, v_proj, k))
+        s, t = _compare(out[k], ora, "attention %s v_proj %s %s utt %d" % (mode, v_proj, variant, k))
         same, ties = same + s, ties + t
-    print("attention %s, v_proj %s: identical 1-best %d/%d, ties %d" % (mode, v_proj, same, len(lens), ties))
+    print("attention %s, v_proj %s, %s: identical 1-best %d/%d, ties %d" % (mode, v_proj, variant or "default", same, len(lens), ties))
     assert same >= len(lens) - 1
 
 

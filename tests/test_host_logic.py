@@ -36,8 +36,9 @@ def test_beam_decoder_constructor_surface(tmp_path):
     assert h.outIndex == [5, 6, 1] and float(h.avgScore()) == -2.0 and len(h.output_scores) == 3
 
 
-@pytest.mark.parametrize("mode,v_proj", [("loc", False), ("dot", False), ("loc", True)])
-def test_batched_stepper_matches_per_hypothesis_modules(mode, v_proj):
+@pytest.mark.parametrize("mode,v_proj,variant", [("loc", False, ""), ("dot", False, ""), ("loc", True, ""),
+                                                 ("loc", False, "yaml_encoder"), ("loc", False, "gru"), ("loc", False, "concat_ln")])
+def test_batched_stepper_matches_per_hypothesis_modules(mode, v_proj, variant):
     """The batched model step against the modules called one hypothesis at a time, as the reference does (decode.py:105-123,
     144-151): location-aware and scaled-dot attention (config key attention.mode), with and without the value projection."""
     import copy
@@ -45,6 +46,14 @@ def test_batched_stepper_matches_per_hypothesis_modules(mode, v_proj):
     from e2e_asr_pytorch_b200.stepper import BatchedStepper
     cfg = copy.deepcopy(synth.TINY_ASR_CFG)
     cfg["attention"]["mode"], cfg["attention"]["v_proj"] = mode, v_proj
+    if variant == "yaml_encoder":         # config/librispeech_asr.yaml as written: no VGG, the second layer drops every other frame
+        cfg["encoder"].update({"vgg": 0, "sample_rate": [1, 2], "sample_style": "drop"})
+    elif variant == "gru":                # GRU encoder layers and a 2-layer GRU speller
+        cfg["encoder"]["module"] = "GRU"
+        cfg["decoder"].update({"module": "GRU", "layer": 2})
+    elif variant == "concat_ln":          # frame concatenation instead of dropping, layer norm on (the reference's projection
+        # layer is Linear(rnn_out, rnn_out) and cannot follow a concatenation, module.py:1037-1038,1078-1079: proj off)
+        cfg["encoder"].update({"sample_rate": [2, 1], "sample_style": "concat", "layer_norm": [True, True], "proj": [False, False]})
     asr = synth.build_asr(31, cfg, seed=0, peak=4.0)
     lm = synth.build_lm(31, synth.TINY_LM_CFG, seed=1)
     lens, beam = [64, 120, 92], 3
