@@ -298,3 +298,39 @@ def test_empty_shard_decodes_to_nothing_without_a_device():
     tok, sc, ln, avg, n = dec.decode_batch_from_host(feat, fl, "cuda:0", return_arrays=True)
     assert tok.shape == (0, 4, 1) and sc.shape == (0, 4, 1) and ln.shape == (0, 4) and avg.shape == (0, 4) and n.shape == (0,)
     assert dec.last_stats["utterances"] == 0 and dec.last_h2d_bytes == 0
+
+
+def test_shard_pack_unpack_property():
+    """Property test (hypothesis) of the multi-GPU host logic: for any lengths, beam, ratio and world size — including more
+    ranks than utterances — the shards partition the set, every rank's ragged buffer has the common size, and packing each
+    shard in any batch order then unpacking the concatenation returns every utterance's N-best in utterance order."""
+    from hypothesis import given, settings, strategies as st
+    from e2e_asr_pytorch_b200 import shard
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(st.integers(min_value=1, max_value=60), min_size=1, max_size=12), st.integers(1, 4), st.integers(1, 5),
+           st.sampled_from([0.07, 0.2, 0.5]), st.integers(0, 1000))
+    def check(quarter_lengths, beam, world, ratio, seed):
+        lengths = np.array(quarter_lengths) * 4
+        shards = shard.plan_shards(lengths, world, ratio)
+        assert len(shards) == world
+        assert sorted(int(i) for s in shards for i in s) == list(range(len(lengths)))
+        size = shard.ragged_size(shards, lengths, beam, ratio)
+        rng = np.random.default_rng(seed)
+        bufs = []
+        for ids in shards:
+            order = [int(i) for i in rng.permutation(np.asarray(ids, dtype=np.int64))]
+            if order:
+                out = _fake_decode(lengths, beam, ratio)(order)
+            else:
+                out = (torch.zeros((0, beam, 1), dtype=torch.int32), torch.zeros((0, beam, 1)), torch.zeros((0, beam), dtype=torch.int32),
+                       torch.zeros((0, beam)), torch.zeros((0,), dtype=torch.int32))
+            buf = shard.pack_nbest_ragged(order, *out, ids, lengths, beam, ratio, size)
+            assert buf.shape == (size,)
+            bufs.append(buf)
+        tok, sc, ln, avg, n = shard.unpack_nbest_ragged(torch.cat(bufs), shards, lengths, beam, ratio, size)
+        want = _fake_decode(lengths, beam, ratio)(list(range(len(lengths))))
+        for a, b in zip((tok, sc, ln, avg, n), want):
+            assert torch.equal(a, b)
+
+    check()
