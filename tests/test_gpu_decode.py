@@ -308,8 +308,9 @@ def test_decode_beam_1(cuda, eos_bias, ctc_w, lm_w, ids):
 
 @pytest.mark.parametrize("mode,v_proj,variant", [("dot", False, ""), ("loc", True, ""), ("loc", False, "yaml_encoder"), ("loc", False, "gru")])
 def test_decode_other_model_configurations(cuda, mode, v_proj, variant):
-    """The reference's other model settings decode like the oracle: attention.mode = 'dot' (scaled-dot energies, plain PyTorch
-    in the batched stepper), attention.v_proj (projected values in the fused location-aware kernel), the encoder of
+    """The reference's other model settings decode like the oracle (pinned to the reference for these settings in
+    tests/test_oracle_vs_reference.py): attention.mode = 'dot' (scaled-dot energies, plain PyTorch in the batched stepper — an
+    extension: the reference's own beam search raises for this mode, asr.py:331), attention.v_proj (projected values in the fused location-aware kernel), the encoder of
     config/librispeech_asr.yaml as written (no VGG, a layer that drops every other frame: the unpacked encoder path), GRU
     encoder layers and a 2-layer GRU speller (the plain PyTorch cells of the stepper)."""
     import copy

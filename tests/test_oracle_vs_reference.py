@@ -74,6 +74,73 @@ def test_beam_oracle_exact_vs_reference_decoder(tmp_path):
             assert float(a.avgScore()) == float(b.mean_score()) == float(c.mean_score())
 
 
+@pytest.mark.parametrize("variant,beam,lm_w,ctc_w,eos_bias", [
+    ("v_proj", 4, 0.3, 0.5, 0.0), ("yaml_encoder", 4, 0.3, 0.5, 0.0), ("gru", 4, 0.3, 0.5, 0.0),
+    ("concat_ln", 4, 0.3, 0.0, 0.0), ("", 1, 0.0, 0.0, 0.0), ("", 1, 0.3, 0.0, 4.0), ("", 1, 0.3, 0.5, 0.0), ("", 24, 0.0, 0.0, 0.0)])
+def test_beam_oracle_and_product_modules_exact_vs_reference_on_other_configurations(tmp_path, variant, beam, lm_w, ctc_w, eos_bias):
+    """The pin of the configuration branches the GPU tests decode (tests/test_gpu_decode.py): with the same weights the
+    reference's BeamDecoder, the oracle on the reference's modules and the oracle on model.py's modules give the same N-best
+    bit for bit — value projection, the yaml's encoder (no VGG, frame dropping), GRU layers, frame concatenation + layer norm
+    (CTC off: with it this fixture is in the reference's crash envelope, decode.py:252), beam 1 (early return, empty N-best when
+    <eos> wins before min_len, one CTC candidate), beam 24.  Scaled-dot attention is not here: the reference's own beam search
+    cannot run it (see the next test)."""
+    import yaml
+    from oracle import beam_oracle as BO
+    from e2e_asr_pytorch_b200 import synth
+    ref = refload.load()
+    torch.set_num_threads(1)
+    cfg = copy.deepcopy(synth.TINY_ASR_CFG)
+    if variant == "v_proj":
+        cfg["attention"]["v_proj"] = True
+    elif variant == "yaml_encoder":
+        cfg["encoder"].update({"vgg": 0, "sample_rate": [1, 2], "sample_style": "drop"})
+    elif variant == "gru":
+        cfg["encoder"]["module"] = "GRU"
+        cfg["decoder"].update({"module": "GRU", "layer": 2})
+    elif variant == "concat_ln":
+        cfg["encoder"].update({"sample_rate": [2, 1], "sample_style": "concat", "layer_norm": [True, True], "proj": [False, False]})
+    mine = synth.build_asr(31, cfg, seed=0, peak=4.0)
+    with torch.no_grad():
+        mine.decoder.char_trans.bias[1] += eos_bias
+    rasr = ref.ASR(synth.FEAT_DIM, 31, True, **copy.deepcopy(cfg)).eval()
+    rasr.load_state_dict(mine.state_dict())
+    lm = synth.build_lm(31, synth.TINY_LM_CFG, seed=1)
+    torch.save({"model": lm.state_dict()}, str(tmp_path / "lm.pth"))
+    yaml.safe_dump({"model": synth.TINY_LM_CFG}, open(str(tmp_path / "lm.yaml"), "w"))
+    for utt, n in ((0, 64), (1, 120)):
+        feat, fl = synth.utterance(utt, n)[None], torch.LongTensor([n])
+        rdec = ref.BeamDecoder(rasr, None, beam, 0.01, 0.2, lm_path=str(tmp_path / "lm.pth"),
+                               lm_config=str(tmp_path / "lm.yaml"), lm_weight=lm_w, ctc_weight=ctc_w)
+        with torch.no_grad():
+            want = rdec(feat, fl)
+            got_ref_modules = BO.decode_utterance(rasr, feat, fl, beam, 0.01, 0.2, lm=rdec.lm if lm_w > 0 else None,
+                                                  lm_weight=lm_w, ctc_weight=ctc_w)
+            got_our_modules = BO.decode_utterance(mine, feat, fl, beam, 0.01, 0.2, lm=lm if lm_w > 0 else None,
+                                                  lm_weight=lm_w, ctc_weight=ctc_w)
+        assert len(want) == len(got_ref_modules) == len(got_our_modules)
+        if eos_bias > 0:
+            assert len(want) == 0                                   # the empty-N-best fixture
+        for a, b, c in zip(want, got_ref_modules, got_our_modules):
+            assert a.outIndex == b.ids == c.ids
+            assert [float(s) for s in a.output_scores] == [float(s) for s in b.scores] == [float(s) for s in c.scores]
+            assert float(a.avgScore()) == float(b.mean_score()) == float(c.mean_score())
+
+
+def test_reference_beam_search_cannot_run_scaled_dot_attention():
+    """attention.mode = 'dot' trains in the reference but its BeamDecoder raises on the first step: ASR.set_state hands the
+    previous alignment to BaseAttention.set_mem(), which takes none (asr.py:331, module.py:1095).  The product decodes this
+    configuration (tests/test_gpu_decode.py compares it with the oracle on model.py's modules); it is an extension, not a
+    parity case — this test documents why no reference N-best exists for it."""
+    from e2e_asr_pytorch_b200 import synth
+    ref = refload.load()
+    cfg = copy.deepcopy(synth.TINY_ASR_CFG)
+    cfg["attention"]["mode"] = "dot"
+    rasr = ref.ASR(synth.FEAT_DIM, 31, True, **cfg).eval()
+    rdec = ref.BeamDecoder(rasr, None, 2, 0.01, 0.2, ctc_weight=0.5)
+    with torch.no_grad(), pytest.raises(TypeError, match="set_mem"):
+        rdec(synth.utterance(0, 64)[None], torch.LongTensor([64]))
+
+
 def test_reference_checkpoint_layout_loads_into_product_model():
     """Parameter names/shapes of model.py equal the reference's at the BASELINE dims."""
     from e2e_asr_pytorch_b200 import synth
